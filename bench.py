@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py — NIQKI hot path on B200: sketch -> index -> query, whole job per step.
+
+Contract (one JSON line on rank 0):  python bench.py --gpus N --steps K --warmup W
+  N=1 workload = BASELINE.json configs[1]: 10k synthetic 5 Mbp genomes --index, then --query 1k
+  mutated copies, K=31 S=15 W=12 H=4, minjac 0.1 (the value the metric line is quoted with).
+  N>1 = the same shard per GPU (weak scaling): rank r indexes genomes [r*G,(r+1)*G), sketches its
+  slice of the queries, all ranks all-gather the query sketches over NCCL and count them against
+  their own shard; N=8 uses 12.5k genomes + 1250 queries per GPU = configs[2] exactly.
+A step = one full pass: sketch the shard's genomes, build its index, sketch + all-gather the
+queries, count/threshold them.  `value` = bases sketched by all ranks / max-over-ranks step time
+with the sequences resident in HBM; `e2e` = the same job through the host-buffer C ABI calls
+(pinned host sequences copied in, sorted hit lists copied out, every step).
+--impl reference times the reference's own CPU path (oracle/_ref, else the oracle port) on a
+bounded sample with all host threads.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 42
+GENOME_LEN = 5_000_000
+K, S, W, H, J = 31, 15, 12, 4, 0.1
+RATES = (0.001, 0.01, 0.05)
+METRIC = "Gbases/s sketched (index 10k x 5 Mbp genomes + query 1k mutated copies, per GPU shard)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genomes", type=int, default=0, help="genomes per GPU (default: 10000; 12500 at 8 GPUs)")
+    ap.add_argument("--queries", type=int, default=0, help="queries per GPU (default: genomes/10)")
+    ap.add_argument("--genome-len", type=int, default=GENOME_LEN)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-genomes", type=int, default=0, help="genomes per GPU in the e2e leg (default: all that fit host RAM)")
+    return ap.parse_args()
+
+
+def thresholds(rates):
+    return np.array([int(np.ldexp(np.longdouble(r), 64)) if r > 0 else 0 for r in rates], dtype=np.uint64)
+
+
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    cores = os.cpu_count() or 1
+    use_ref = O.ref_available()
+    kind = "reference" if use_ref else "port"
+    o = O.Oracle(K=K, S=S, W=W, H=H, J=J)
+    L = args.genome_len
+    per_core = 4
+    n_idx = max(8, min(cores * per_core, 512))
+    n_q = max(1, n_idx // 10)
+    # sample: n_idx genomes + n_q mutated copies, generated by the (multi-threaded) C generator
+    seqs = [o.synth_genome(g, L) for g in range(n_idx)]
+    seqs += [o.synth_mutant(q % n_idx, q, RATES[q % 3], L) for q in range(n_q)]
+    bases, offs = O.concat_entries(seqs)
+    del seqs
+    nbases = int(offs[-1])
+    if use_ref:
+        r = O.Ref(K=K, S=S, W=W, H=H, J=J)  # 2^27 std::vector headers, ~5 s, untimed
+        sk, _ = r.sketch_batch(bases, offs, nthreads=cores)
+        for g in range(n_idx):
+            r.insert_sketch(sk[g], g, f"g{g}")  # index built once, untimed (Index cannot be reset)
+    else:
+        sk = o.sketch_batch(bases, offs, cores)
+        o.insert_sketches(sk[:n_idx])
+
+    def step():
+        t0 = time.perf_counter()
+        if use_ref:
+            s2, _ = r.sketch_batch(bases, offs, nthreads=cores, want_out=True)
+            tq, _ = r.query_batch_timed(s2[n_idx:], nthreads=cores)
+        else:
+            s2 = o.sketch_batch(bases, offs, cores)
+            o.query_batch(s2[n_idx:], cores)
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(args.steps)]
+    total = sum(times)
+    value = nbases * args.steps / total / 1e9
+    sample = (f"{n_idx} genomes + {n_q} mutated queries of {L} bp per step: compute_sketch on every entry "
+              f"(OpenMP, {cores} threads) + query_sketch of the {n_q} queries against a {n_idx}-genome index built once")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "configs[1] sample: " + sample, "K": K, "S": S, "W": W, "H": H, "minjac": J},
+            "cpu_baseline": {"value": value, "unit": "Gbases/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, cores):
+    """Bounded sample of the same workload on the host cores (rank 0, N=1 only): ~10-30 s of CPU."""
+    from oracle import oracle as O
+
+    use_ref = O.ref_available()
+    o = O.Oracle(K=K, S=S, W=W, H=H, J=J)
+    L = args.genome_len
+    n_idx = max(8, min(cores * 4, 256))
+    n_q = max(1, n_idx // 10)
+    seqs = [o.synth_genome(g, L) for g in range(n_idx)] + [o.synth_mutant(q % n_idx, q, RATES[q % 3], L) for q in range(n_q)]
+    bases, offs = O.concat_entries(seqs)
+    del seqs
+    t0 = time.perf_counter()
+    if use_ref:
+        r = O.Ref(K=K, S=S, W=W, H=H, J=J)
+        sk, secs = r.sketch_batch(bases, offs, nthreads=cores)
+        for g in range(n_idx):
+            r.insert_sketch(sk[g], g, f"g{g}")
+        tq, _ = r.query_batch_timed(sk[n_idx:], nthreads=cores)
+        r.close()
+    else:
+        t1 = time.perf_counter()
+        sk = o.sketch_batch(bases, offs, cores)
+        secs = time.perf_counter() - t1
+        o.insert_sketches(sk[:n_idx])
+        t1 = time.perf_counter()
+        o.query_batch(sk[n_idx:], cores)
+        tq = time.perf_counter() - t1
+    return {"value": int(offs[-1]) / secs / 1e9, "unit": "Gbases/s", "cores": cores,
+            "kind": "reference" if use_ref else "port",
+            "sample": f"compute_sketch on {n_idx}+{n_q} entries of {L} bp ({int(offs[-1])/1e9:.2f} Gbases) with {cores} threads",
+            "query_sketches_per_s": n_q / tq if tq > 0 else None,
+            "query_sample": f"query_sketch of {n_q} queries vs a {n_idx}-genome index, {cores} threads",
+            "wall_s": time.perf_counter() - t0}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import niqki_b200
+    from niqki_b200.capi import check, lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    G = args.genomes or (12500 if world == 8 else 10000)
+    Q = args.queries or max(1, G // 10)
+    L = args.genome_len
+    Lp = (L + 15) // 16 * 16  # entries start 16-byte aligned in HBM
+    Lc = lib()
+    stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream shared by torch and the library
+    torch.cuda.set_stream(stream)
+    ctx = niqki_b200.Context(local, stream)
+    ix = niqki_b200.Index(S=S, K=K, W=W, H=H, min_fract=J, ctx=ctx)
+    F = ix.F
+
+    # ---- synthetic inputs, generated in HBM (untimed)
+    g0 = rank * G
+    q0 = rank * Q
+    d_idx = torch.empty(G * L + 64, dtype=torch.uint8, device=dev)
+    check(Lc.nq_synth_genomes_device(ctx.h, SEED, g0, G, L, C.c_void_p(d_idx.data_ptr())))
+    qid = np.arange(q0, q0 + Q, dtype=np.uint64)
+    parents = (qid % np.uint64(G * world)).astype(np.uint64)  # queries are copies of genomes 0..Q*world-1
+    thr = thresholds([RATES[int(q) % 3] for q in qid])
+    d_qry = torch.empty(Q * L + 64, dtype=torch.uint8, device=dev)
+    check(Lc.nq_synth_mutants_device(ctx.h, SEED, parents.ctypes.data, qid.ctypes.data, thr.ctypes.data, Q, L,
+                                     C.c_void_p(d_qry.data_ptr())))
+    idx_offs = np.arange(G + 1, dtype=np.uint64) * L
+    qry_offs = np.arange(Q + 1, dtype=np.uint64) * L
+    sk_idx = torch.empty((G, F), dtype=torch.int32, device=dev)
+    sk_qry = torch.empty((Q, F), dtype=torch.int32, device=dev)
+    sk_all = torch.empty((Q * world, F), dtype=torch.int32, device=dev) if world > 1 else sk_qry
+    fl_idx = torch.empty(G, dtype=torch.int32, device=dev)
+    fl_qry = torch.empty(Q, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        ix.compute_sketches(d_idx, idx_offs, out=sk_idx, flags=fl_idx)
+        ix.insert_sketches(sk_idx, gid_base=g0)
+        ix.compute_sketches(d_qry, qry_offs, out=sk_qry, flags=fl_qry)
+        if world > 1:
+            dist.all_gather_into_tensor(sk_all, sk_qry)
+        ix.query_sketches(sk_all, fetch=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    ctx.set_timing(True)
+    ctx.timing_reset()
+    launches0 = ctx.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    kt = ctx.timing()
+    launches = ctx.launches - launches0
+    gathered = ctx.last_query_gathered
+    ctx.set_timing(False)
+    bases_per_step = (G + Q) * L * world
+    value = bases_per_step * args.steps / (ms_total / 1e3) / 1e9
+    info = ix.info()
+
+    # ---- correctness spot check (untimed): parents are found, counts match the device sketches
+    ptr, cnt, gid = ix.query_sketches(sk_all[: min(8, Q)])
+    first_hits = [int(gid[int(ptr[i])]) if ptr[i + 1] > ptr[i] else -1 for i in range(min(8, Q))]
+
+    # ---- e2e: the same job through the host-buffer C ABI (H2D of the sequences, D2H of sketches
+    # for the index call and of the sorted hit lists), on as many genomes as the host can pin
+    e2e = None
+    if not args.no_e2e:
+        avail = mem_available_bytes()
+        Ge = args.e2e_genomes or G
+        need = (Ge + Q) * L + (Ge + Q) * F * 4
+        while Ge > 64 and avail and need * 1.3 > avail:
+            Ge //= 2
+            need = (Ge + Q) * L + (Ge + Q) * F * 4
+        Qe = max(1, min(Q, Ge // 10))
+        h_idx = torch.empty(Ge * L, dtype=torch.uint8, pin_memory=True)
+        h_qry = torch.empty(Qe * L, dtype=torch.uint8, pin_memory=True)
+        h_idx.copy_(d_idx[: Ge * L]); h_qry.copy_(d_qry[: Qe * L])
+        h_sk_idx = torch.empty((Ge, F), dtype=torch.int32, pin_memory=True)
+        h_sk_qry = torch.empty((Qe, F), dtype=torch.int32, pin_memory=True)
+        torch.cuda.synchronize()
+        n_idx_b, n_qry_b = h_idx.numpy(), h_qry.numpy()
+        n_sk_idx, n_sk_qry = h_sk_idx.numpy(), h_sk_qry.numpy()
+        eo_idx = np.arange(Ge + 1, dtype=np.uint64) * L
+        eo_qry = np.arange(Qe + 1, dtype=np.uint64) * L
+        d2h = [0]
+
+        def step_e2e():
+            ix.compute_sketches(n_idx_b, eo_idx, out=n_sk_idx)      # H2D bases, D2H sketches
+            ix.insert_sketches(n_sk_idx, gid_base=g0)               # H2D sketches
+            ix.compute_sketches(n_qry_b, eo_qry, out=n_sk_qry)
+            p_, c_, g_ = ix.query_sketches(n_sk_qry)                # H2D sketches, D2H sorted hits
+            d2h[0] = n_sk_idx.nbytes + n_sk_qry.nbytes + c_.nbytes + g_.nbytes + p_.nbytes
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            step_e2e()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_bases = (Ge + Qe) * L * world
+        e2e = {"value": e2e_bases * e2e_steps / float(dt.item()) / 1e9, "unit": "Gbases/s",
+               "h2d_bytes_per_step": int((Ge + Qe) * L + (Ge + Qe) * F * 4), "d2h_bytes_per_step": int(d2h[0]),
+               "genomes": Ge, "queries": Qe, "steps": e2e_steps,
+               "note": "nq_sketch_batch / nq_index_build / nq_query_batch with pinned host buffers; no inter-rank exchange in this leg"}
+        del h_idx, h_qry, h_sk_idx, h_sk_qry
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        scan_ms, scan_n = kt["scan"]
+        q_ms, q_n = kt["query"]
+        bases_per_scan = (G + Q) * L * args.steps / max(scan_n, 1)
+        scan_gbs = bases_per_scan / (scan_ms / max(scan_n, 1) / 1e3) / 1e9 if scan_ms else None
+        nq_total = Q * world
+        q_bytes = 4 * gathered + nq_total * F * (8 + 4)  # + 8 B per hit (negligible at minjac 0.1)
+        q_gbs = q_bytes / (q_ms / max(q_n, 1) / 1e3) / 1e9 if q_ms else None
+        sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"configs[{2 if world == 8 else 1}]: {G} synthetic {L} bp genomes --index + {Q} mutated "
+                                   f"copies --query per GPU, x{world} GPUs",
+                       "K": K, "S": S, "W": W, "H": H, "minjac": J, "genomes_per_gpu": G, "queries_per_gpu": Q,
+                       "l2": "inputs larger than L2 (>= 50 GB of sequence per step)", "parallelism": f"shard-by-gid x{world}"},
+            "query_sketches_per_s": nq_total / (q_ms / max(q_n, 1) / 1e3) if q_ms else None,
+            "index_postings": info["n_postings"],
+            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt.items()},
+            "roofline": {"kernel": "sketch_scan_kernel", "bound": "hbm", "achieved": scan_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": (scan_gbs / hbm_peak) if scan_gbs else None, "traffic": None,
+                         "peak_source": peak_src,
+                         "note": "1 B/base algorithmic; the kernel is integer-ALU bound (see roofline_alu)"},
+            "roofline_alu": {"kernel": "sketch_scan_kernel", "bound": "int32 issue", "unit": "Gbases/s",
+                             "achieved": scan_gbs,
+                             "peak": 148 * 4 * sm_clk * 1e6 * 32 / 57 / 1e9,
+                             "note": "peak = 148 SMs x 4 schedulers x 1 warp-instr/clk at the sampled SM clock / 57 SASS instr per base"},
+            "roofline_query": {"kernel": "query_count_kernel", "bound": "hbm", "achieved": q_gbs, "peak": hbm_peak,
+                               "unit": "GB/s", "frac": (q_gbs / hbm_peak) if q_gbs else None, "traffic": None,
+                               "algorithmic_bytes": q_bytes, "gathered_postings": gathered},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "first_hits": first_hits,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline(args, os.cpu_count() or 1)
+            except Exception as exc:  # the baseline must never take the bench line down
+                line["cpu_baseline"] = {"error": repr(exc)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,344 @@
+// capi.cu — the C ABI of libniqki_b200.so (include/niqki_b200.h): parameter block, context,
+// host-buffer entry points (copies pipelined against the kernels) and thin forwards to the
+// device-pointer implementations in sketch.cu / index.cu / query.cu / matrix.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "internal.h"
+
+static thread_local char g_err[1024] = "";
+
+int nq_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+extern "C" const char* nq_last_error(void) { return g_err; }
+extern "C" const char* nq_version(void) { return "niqki_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------- parameters (host scalar code)
+
+// Index::Index — /root/reference/src/niqki_index.cpp:13-29
+extern "C" int nq_params_init(nq_params* p, uint32_t K, uint32_t S, uint32_t W, uint32_t H, double min_fract) {
+  if (!p) return nq_set_error(NQ_ERR_INVALID, "null params");
+  // limits of the reference: 1<<2K in 64 bits, 32-bit fingerprint_range*F
+  if (K < 2 || K > 31) return nq_set_error(NQ_ERR_INVALID, "K=%u outside [2,31]", K);
+  if (S < 1 || W < 1 || W + S >= 32) return nq_set_error(NQ_ERR_INVALID, "need S>=1, W>=1, W+S<32 (S=%u W=%u)", S, W);
+  if (H > W) return nq_set_error(NQ_ERR_INVALID, "H=%u > W=%u", H, W);
+  p->K = K; p->S = S; p->W = W; p->H = H;
+  p->F = 1u << S;
+  p->M = W - H;
+  p->min_score = (uint32_t)(min_fract * (double)p->F);
+  p->range = (int32_t)(1u << W);
+  p->mask_M = (1u << p->M) - 1u;
+  p->maxrem = (1u << H) - 1u;
+  return NQ_OK;
+}
+
+// Index::score_H — src/niqki_index.cpp:142-164 (double arithmetic, evaluated once on the host)
+static double score_h(uint32_t W, double x, int h) {
+  const double eps = 0.02, m = (double)W - h, two_h = std::pow(2, h);
+  auto bound = [&](double base) {
+    const double u = ((double)1 - std::pow(base, 1 / x)) * std::pow(2, 64);
+    const double i = std::log2(u) + two_h - 64;
+    const double j = u * std::pow(2, m - 64 - i + two_h);
+    if (u < std::pow(2, 64 - two_h + 1)) return u * std::pow(2, two_h - 64 - ((double)W - h) - 1);
+    return i * std::pow(2, m) + j;
+  };
+  return bound(eps) - bound(1 - eps);
+}
+
+// Index::select_best_H — src/niqki_index.cpp:126-138.  Only H and M change; mask_M and maxrem keep
+// their construction-time values, exactly like the reference.
+extern "C" int nq_params_select_best_H(nq_params* p, double genome_size) {
+  if (!p) return nq_set_error(NQ_ERR_INVALID, "null params");
+  const double x = genome_size / (double)p->F;
+  double best = 0;
+  for (uint32_t h = 2; h < 7; ++h) {
+    const double s = score_h(p->W, x, (int)h);
+    if (s > best) {
+      best = s;
+      p->H = h;
+    }
+  }
+  p->M = p->W - p->H;
+  return NQ_OK;
+}
+
+int nq_params_check(const nq_params* p) {
+  if (!p) return nq_set_error(NQ_ERR_INVALID, "null params");
+  if (p->K < 2 || p->K > 31 || p->S < 1 || p->W < 1 || p->W + p->S >= 32 || p->F != (1u << p->S) ||
+      p->range != (int32_t)(1u << p->W) || p->M >= 32)
+    return nq_set_error(NQ_ERR_INVALID, "inconsistent parameter block (K=%u S=%u W=%u M=%u F=%u)", p->K, p->S, p->W,
+                        p->M, p->F);
+  return NQ_OK;
+}
+
+// ---------------------------------------------------------------- context
+
+static void nq_timing_resolve(nq_ctx* ctx);
+
+extern "C" int nq_device_count(int* count) {
+  if (!count) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  *count = 0;
+  NQ_CUDA(cudaGetDeviceCount(count));
+  return NQ_OK;
+}
+
+extern "C" int nq_ctx_create(int device, void* cuda_stream, nq_ctx** out) {
+  if (!out) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int count = 0;
+  NQ_CUDA(cudaGetDeviceCount(&count));
+  if (count == 0) return nq_set_error(NQ_ERR_CUDA, "no CUDA device: libniqki_b200 has no CPU fallback");
+  if (device < 0 || device >= count) return nq_set_error(NQ_ERR_INVALID, "device %d outside [0,%d)", device, count);
+  NQ_CUDA(cudaSetDevice(device));
+  nq_ctx* ctx = new nq_ctx();
+  ctx->device = device;
+  if (cuda_stream) {
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  } else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete ctx;
+      return nq_set_error(NQ_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    ctx->own_stream = true;
+  }
+  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  }
+  // keep freed scratch in the pool instead of returning it to the driver after every call
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  *out = ctx;
+  return NQ_OK;
+}
+
+extern "C" int nq_ctx_destroy(nq_ctx* ctx) {
+  if (!ctx) return NQ_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  nq_timing_resolve(ctx);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return NQ_OK;
+}
+
+extern "C" int nq_ctx_sync(nq_ctx* ctx) {
+  if (!ctx) return nq_set_error(NQ_ERR_INVALID, "null context");
+  NQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NQ_OK;
+}
+
+extern "C" uint64_t nq_ctx_launch_count(const nq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static void nq_timing_resolve(nq_ctx* ctx) {
+  for (auto& t : ctx->timed) {
+    float ms = 0;
+    if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+      ctx->kind_ms[t.kind] += ms;
+      ctx->kind_n[t.kind]++;
+    }
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  ctx->timed.clear();
+}
+
+extern "C" int nq_ctx_set_timing(nq_ctx* ctx, int on) {
+  if (!ctx) return nq_set_error(NQ_ERR_INVALID, "null context");
+  ctx->timing = on != 0;
+  return NQ_OK;
+}
+extern "C" int nq_ctx_timing(nq_ctx* ctx, int kind, double* ms, uint64_t* launches) {
+  if (!ctx || kind < 0 || kind >= 8) return nq_set_error(NQ_ERR_INVALID, "bad timing query");
+  nq_timing_resolve(ctx);
+  if (ms) *ms = ctx->kind_ms[kind];
+  if (launches) *launches = ctx->kind_n[kind];
+  return NQ_OK;
+}
+extern "C" int nq_ctx_timing_reset(nq_ctx* ctx) {
+  if (!ctx) return nq_set_error(NQ_ERR_INVALID, "null context");
+  nq_timing_resolve(ctx);
+  for (int k = 0; k < 8; ++k) { ctx->kind_ms[k] = 0; ctx->kind_n[k] = 0; }
+  return NQ_OK;
+}
+extern "C" uint64_t nq_ctx_last_query_gathered(const nq_ctx* ctx) { return ctx ? ctx->last_query_gathered : 0; }
+
+extern "C" void* nq_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    nq_set_error(NQ_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void nq_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------- sketching
+
+extern "C" int nq_sketch_batch_device(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint64_t bases_capacity,
+                                      const uint64_t* offsets, uint64_t n, int32_t* d_sketches, uint32_t* d_flags) {
+  if (!ctx || !offsets || (n && (!d_bases || !d_sketches))) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  NQ_CUDA(cudaSetDevice(ctx->device));
+  return nq_launch_sketch(ctx, p, d_bases, bases_capacity, offsets, n, d_sketches, d_flags);
+}
+
+extern "C" int nq_densify_device(nq_ctx* ctx, const nq_params* p, int32_t* d_sketches, uint64_t n, uint32_t* d_flags) {
+  if (!ctx || (n && !d_sketches)) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  NQ_CUDA(cudaSetDevice(ctx->device));
+  return nq_launch_densify(ctx, p, d_sketches, n, d_flags);
+}
+
+// Host-buffer form: entries are grouped into device batches; batch i+1's characters are copied
+// (copy stream) while batch i is sketched (compute stream), and batch i's sketches travel back
+// while batch i+1 runs.
+extern "C" int nq_sketch_batch(nq_ctx* ctx, const nq_params* p, const char* bases, const uint64_t* offsets, uint64_t n,
+                               int32_t* sketches, uint32_t* flags) {
+  if (!ctx || !offsets || (n && (!bases || !sketches))) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  NQ_TRY(nq_params_check(p));
+  NQ_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return NQ_OK;
+  const uint64_t F = p->F;
+  const uint64_t max_bases = 512ull << 20, max_cells = (1ull << 30) / 4;  // per batch: 512 MB in, 1 GB out
+  // batch boundaries
+  std::vector<uint64_t> cut{0};
+  {
+    uint64_t b0 = 0;
+    for (uint64_t e = 0; e < n; ++e) {
+      const bool full = (offsets[e + 1] - offsets[b0] > max_bases || (e + 1 - b0) * F > max_cells) && e > b0;
+      if (full) {
+        cut.push_back(e);
+        b0 = e;
+      }
+    }
+    cut.push_back(n);
+  }
+  uint64_t cap_bases = 0, cap_entries = 0;
+  for (size_t b = 0; b + 1 < cut.size(); ++b) {
+    cap_bases = std::max(cap_bases, offsets[cut[b + 1]] - offsets[cut[b]]);
+    cap_entries = std::max(cap_entries, cut[b + 1] - cut[b]);
+  }
+  cap_bases = (cap_bases + 15 + 16) & ~15ull;
+  struct Slot {
+    char* d_bases = nullptr;
+    int32_t* d_sk = nullptr;
+    uint32_t* d_flags = nullptr;
+    cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
+    std::vector<uint64_t> local_off;
+  } slot[2];
+  int st = NQ_OK;
+  cudaError_t e = cudaSuccess;
+  const int nslots = cut.size() > 2 ? 2 : 1;
+  for (int s = 0; s < nslots && e == cudaSuccess; ++s) {
+    if ((e = cudaMalloc((void**)&slot[s].d_bases, cap_bases)) != cudaSuccess) break;
+    if ((e = cudaMalloc((void**)&slot[s].d_sk, cap_entries * F * 4)) != cudaSuccess) break;
+    if ((e = cudaMalloc((void**)&slot[s].d_flags, cap_entries * 4)) != cudaSuccess) break;
+    cudaEventCreateWithFlags(&slot[s].h2d, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&slot[s].done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&slot[s].d2h, cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) st = nq_set_error(NQ_ERR_CUDA, "sketch batch allocation failed: %s", cudaGetErrorString(e));
+  for (size_t b = 0; st == NQ_OK && b + 1 < cut.size(); ++b) {
+    Slot& s = slot[b % nslots];
+    const uint64_t e0 = cut[b], e1 = cut[b + 1], nb = e1 - e0, base0 = offsets[e0], nbytes = offsets[e1] - base0;
+    if (b >= (size_t)nslots) cudaEventSynchronize(s.d2h);  // slot's previous results are out
+    s.local_off.resize(nb + 1);
+    for (uint64_t i = 0; i <= nb; ++i) s.local_off[i] = offsets[e0 + i] - base0;
+    if (nbytes) e = cudaMemcpyAsync(s.d_bases, bases + base0, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e != cudaSuccess) { st = nq_set_error(NQ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
+    cudaEventRecord(s.h2d, ctx->copy_stream);
+    cudaStreamWaitEvent(ctx->stream, s.h2d, 0);
+    st = nq_launch_sketch(ctx, p, s.d_bases, cap_bases, s.local_off.data(), nb, s.d_sk, s.d_flags);
+    if (st != NQ_OK) break;
+    cudaEventRecord(s.done, ctx->stream);
+    cudaStreamWaitEvent(ctx->copy_stream, s.done, 0);
+    e = cudaMemcpyAsync(sketches + e0 * F, s.d_sk, nb * F * 4, cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e == cudaSuccess && flags)
+      e = cudaMemcpyAsync(flags + e0, s.d_flags, nb * 4, cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e != cudaSuccess) { st = nq_set_error(NQ_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); break; }
+    cudaEventRecord(s.d2h, ctx->copy_stream);
+  }
+  if ((e = cudaStreamSynchronize(ctx->copy_stream)) != cudaSuccess && st == NQ_OK)
+    st = nq_set_error(NQ_ERR_CUDA, "sketch batch failed: %s", cudaGetErrorString(e));
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess && st == NQ_OK)
+    st = nq_set_error(NQ_ERR_CUDA, "sketch batch failed: %s", cudaGetErrorString(e));
+  for (int s = 0; s < 2; ++s) {
+    cudaFree(slot[s].d_bases); cudaFree(slot[s].d_sk); cudaFree(slot[s].d_flags);
+    if (slot[s].h2d) cudaEventDestroy(slot[s].h2d);
+    if (slot[s].done) cudaEventDestroy(slot[s].done);
+    if (slot[s].d2h) cudaEventDestroy(slot[s].d2h);
+  }
+  return st;
+}
+
+// ---------------------------------------------------------------- index / query / matrix
+
+extern "C" int nq_index_build_device(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketches, uint64_t n,
+                                     uint32_t gid_base, nq_index** out) {
+  if (!ctx || !d_sketches || !out) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  NQ_CUDA(cudaSetDevice(ctx->device));
+  return nq_index_build_impl(ctx, p, d_sketches, n, gid_base, out);
+}
+
+extern "C" int nq_index_build(nq_ctx* ctx, const nq_params* p, const int32_t* sketches, uint64_t n, uint32_t gid_base,
+                              nq_index** out) {
+  if (!ctx || !sketches || !out) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  NQ_TRY(nq_params_check(p));
+  NQ_CUDA(cudaSetDevice(ctx->device));
+  int32_t* d = nullptr;
+  const size_t bytes = (size_t)n * p->F * 4;
+  NQ_TRY(nq_dmalloc(ctx, (void**)&d, bytes));
+  cudaError_t e = cudaMemcpyAsync(d, sketches, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  int st = e == cudaSuccess ? nq_index_build_impl(ctx, p, d, n, gid_base, out)
+                            : nq_set_error(NQ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  nq_dfree(ctx, d);
+  return st;
+}
+
+extern "C" int nq_query_batch_device(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t min_score,
+                                     nq_hits** out) {
+  if (!ix || (nq && !d_sketches)) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  NQ_CUDA(cudaSetDevice(ix->ctx->device));
+  return nq_query_impl(ix, d_sketches, nq, min_score, out);
+}
+
+extern "C" int nq_query_batch(nq_index* ix, const int32_t* sketches, uint64_t nq, uint32_t min_score, nq_hits** out) {
+  if (!ix || !out || (nq && !sketches)) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  nq_ctx* ctx = ix->ctx;
+  NQ_CUDA(cudaSetDevice(ctx->device));
+  int32_t* d = nullptr;
+  const size_t bytes = (size_t)nq * ix->p.F * 4;
+  NQ_TRY(nq_dmalloc(ctx, (void**)&d, bytes));
+  cudaError_t e = bytes ? cudaMemcpyAsync(d, sketches, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+  int st = e == cudaSuccess ? nq_query_impl(ix, d, nq, min_score, out)
+                            : nq_set_error(NQ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  nq_dfree(ctx, d);
+  return st;
+}
+
+extern "C" uint64_t nq_hits_total(const nq_hits* h) { return h ? h->counts.size() : 0; }
+extern "C" const uint64_t* nq_hits_ptr(const nq_hits* h) { return h ? h->ptr.data() : nullptr; }
+extern "C" const uint32_t* nq_hits_counts(const nq_hits* h) { return h ? h->counts.data() : nullptr; }
+extern "C" const uint32_t* nq_hits_gids(const nq_hits* h) { return h ? h->gids.data() : nullptr; }
+extern "C" void nq_hits_free(nq_hits* h) { delete h; }
+
+extern "C" int nq_matrix_rows(nq_index* ix, uint32_t row_begin, uint32_t row_end, int wrap16, uint32_t* counts) {
+  if (!ix) return nq_set_error(NQ_ERR_INVALID, "null index");
+  NQ_CUDA(cudaSetDevice(ix->ctx->device));
+  return nq_matrix_impl(ix, row_begin, row_end, wrap16, counts);
+}

@@ -1,0 +1,105 @@
+// internal.h — host-side declarations shared by the .cu files of libniqki_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "niqki_b200.h"
+
+struct nq_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;  // compute stream (owned or borrowed)
+  bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;  // H2D / D2H pipeline stream (owned)
+  int sm_count = 148;
+  size_t smem_optin = 0;  // max dynamic shared memory per block (opt-in)
+  uint64_t launches = 0;  // kernels launched through this context
+  // optional per-kernel device timing (nq_ctx_set_timing): event pairs resolved at report time
+  bool timing = false;
+  struct Timed { int kind; cudaEvent_t a, b; };
+  std::vector<Timed> timed;
+  double kind_ms[8] = {0};
+  uint64_t kind_n[8] = {0};
+  uint64_t last_query_gathered = 0;  // gids gathered by the last query call (roofline numerator)
+};
+
+enum NqKernelKind { NQK_SCAN = 0, NQK_DENSIFY = 1, NQK_TRANSPOSE = 2, NQK_CELLSORT = 3, NQK_QUERY = 4, NQK_MATRIX = 5 };
+
+// RAII bracket: records an event pair around a kernel launch when timing is on
+struct NqTimer {
+  nq_ctx* ctx; int kind; cudaEvent_t a = nullptr, b = nullptr;
+  NqTimer(nq_ctx* c, int k) : ctx(c), kind(k) {
+    if (ctx->timing) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, ctx->stream); }
+  }
+  ~NqTimer() {
+    if (a) { cudaEventRecord(b, ctx->stream); ctx->timed.push_back({kind, a, b}); }
+  }
+};
+
+int nq_set_error(int code, const char* fmt, ...);
+
+#define NQ_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return nq_set_error(NQ_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,    \
+                          cudaGetErrorString(_e));                                             \
+  } while (0)
+
+#define NQ_TRY(expr)            \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != NQ_OK) return _s; \
+  } while (0)
+
+#define NQ_CHECK_LAUNCH(ctx)       \
+  do {                             \
+    (ctx)->launches++;             \
+    NQ_CUDA(cudaPeekAtLastError()); \
+  } while (0)
+
+// stream-ordered scratch allocation
+inline int nq_dmalloc(nq_ctx* ctx, void** p, size_t bytes) {
+  NQ_CUDA(cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream));
+  return NQ_OK;
+}
+inline void nq_dfree(nq_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+int nq_params_check(const nq_params* p);
+
+// ---- sketch.cu
+int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint64_t bases_capacity,
+                     const uint64_t* h_offsets, uint64_t n, int32_t* d_sketches, uint32_t* d_flags);
+int nq_launch_densify(nq_ctx* ctx, const nq_params* p, int32_t* d_sketches, uint64_t n, uint32_t* d_flags);
+
+// ---- index.cu / query.cu / matrix.cu
+struct nq_index {
+  nq_ctx* ctx = nullptr;
+  nq_params p{};
+  uint32_t n = 0;         // genomes in this shard
+  uint32_t gid_base = 0;  // gid of local genome 0
+  uint32_t n_stride = 0;  // slots per cell in d_gids
+  uint64_t n_postings = 0;
+  // CSR with a fixed cell stride: list (cell, fp) = d_gids[cell*n_stride + row[cell*(range+1)+fp] ..
+  //                                                          row[cell*(range+1)+fp+1])
+  uint32_t* d_row = nullptr;   // [F][range+1]
+  uint32_t* d_gids = nullptr;  // [F][n_stride], global gids
+  // device-resident results of the last nq_query_batch_device(out == NULL)
+  uint64_t* d_pool = nullptr;
+  uint64_t pool_cap = 0;
+};
+
+struct nq_hits {
+  std::vector<uint64_t> ptr;
+  std::vector<uint32_t> counts, gids;
+};
+
+int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketches, uint64_t n,
+                        uint32_t gid_base, nq_index** out);
+int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t min_score, nq_hits** out);
+int nq_matrix_impl(nq_index* ix, uint32_t row_begin, uint32_t row_end, int wrap16, uint32_t* h_counts);

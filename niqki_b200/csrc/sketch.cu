@@ -1,0 +1,364 @@
+// sketch.cu — K1+K2: rolling canonical k-mer hash + one-permutation bucket-min sketch, and K2b:
+// densification.  Replaces Index::compute_sketch / sketch_densification and the helpers under
+// them (/root/reference/src/niqki_index.cpp:114-123, 211-236, 240-273, 277-358).
+//
+// Scan kernel layout: one CTA per span (= a whole entry, or a slice of a long one).  The CTA keeps
+// the 2^S-cell sketch in shared memory (u32, 0xFFFFFFFF = empty = int32 -1), every thread streams
+// its own contiguous run of the span straight from HBM with 16-byte loads (the kernel is
+// integer-ALU bound: ~1 byte of DRAM traffic per ~45 integer ops), and the per-CTA sketch is
+// merged into the entry's sketch in HBM with atomicMin — bucket-min is associative and
+// commutative, so slicing is exact (SURVEY.md App. A3 "Chunking").
+#include <algorithm>
+#include <vector>
+
+#include "device_common.cuh"
+#include "internal.h"
+
+namespace nq {
+
+struct Span {
+  uint64_t kb;     // first k-mer start of the span (byte offset into the bases buffer)
+  uint64_t ke;     // one past the last k-mer start
+  uint64_t e0;     // first byte of the entry
+  uint32_t entry;  // sketch row
+  uint32_t pad;
+};
+
+// char -> (forward code, complement code pre-shifted to its place in the reverse strand).
+// nuc2int (:114-123): C,G,T -> 1,2,3, anything else 0.  nuc2intrc (:211-221): A,C,G -> 3,2,1,
+// anything else 0.  Upper case only; every other byte is 0 on BOTH strands.
+__device__ __forceinline__ uint32_t fw_code(uint32_t c) { return c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 0u; }
+__device__ __forceinline__ uint32_t rv_code(uint32_t c) { return c == 'A' ? 3u : c == 'C' ? 2u : c == 'G' ? 1u : 0u; }
+
+// str2numstrand (:255-273) accepts both cases; returns 4 for a foreign byte.
+__device__ __forceinline__ uint32_t seed_code(uint32_t c) {
+  switch (c) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return 4;
+  }
+}
+
+struct KmerState {
+  uint64_t f, r;
+};
+
+template <bool SMEM>
+struct SketchSink {
+  uint32_t* sk;  // shared (SMEM) or global sketch row
+  __device__ __forceinline__ void update(uint32_t b, uint32_t fp) const {
+    // sketch[b] = min(sketch[b], fp) with empty = 0xFFFFFFFF (:350-355).  A plain read filters out
+    // the ~95% of k-mers that cannot lower the cell; a stale read only makes the filter
+    // conservative because cells never increase.
+    if (fp < sk[b]) atomicMin(&sk[b], fp);
+  }
+};
+
+template <bool SMEM, int NT>
+__global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __restrict__ bases,
+                                                         const uint64_t* __restrict__ offsets,
+                                                         const Span* __restrict__ spans, uint32_t* gsk,
+                                                         DevParams P) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint2* lut = reinterpret_cast<uint2*>(smem);  // [256] {fw, rv << (rc_shift or rc_shift-32)}
+  uint32_t* ssk = smem + 512;                   // [F] when SMEM
+
+  uint64_t A, B, E0;
+  uint32_t entry;
+  if (spans) {
+    const Span s = spans[blockIdx.x];
+    A = s.kb; B = s.ke; E0 = s.e0; entry = s.entry;
+  } else {
+    entry = blockIdx.x;
+    E0 = offsets[entry];
+    const uint64_t E1 = offsets[entry + 1];
+    A = E0;
+    B = (E1 - E0 > P.K) ? E1 - P.K : E0;  // L-K k-mers: the one starting at L-K is skipped (:342, B2)
+  }
+  if (A >= B) return;
+
+  const bool rc_hi = P.rc_shift >= 32;
+  for (uint32_t c = threadIdx.x; c < 256; c += NT) {
+    const uint32_t rv = rv_code(c);
+    lut[c] = make_uint2(fw_code(c), rc_hi ? rv << (P.rc_shift - 32) : rv << P.rc_shift);
+  }
+  uint32_t* grow = gsk + (size_t)entry * P.F;
+  if (SMEM)
+    for (uint32_t i = threadIdx.x; i < P.F; i += NT) ssk[i] = kEmpty;
+  __syncthreads();
+  SketchSink<SMEM> sink{SMEM ? ssk : grow};
+
+  // this thread's run of k-mer starts [lo, hi): 16-byte aligned slices of the span
+  const uint64_t base = A & ~15ull;
+  uint64_t R = ((B - base + NT - 1) / NT + 15) & ~15ull;
+  if (R < 64) R = 64;  // keeps every run but the first clear of the K-1 seed characters
+  const uint64_t lo = max(A, base + (uint64_t)threadIdx.x * R);
+  const uint64_t hi = min(B, base + (uint64_t)(threadIdx.x + 1) * R);
+
+  if (lo < hi) {
+    const uint32_t K = P.K;
+    uint32_t flo = 0, fhi = 0, rlo = 0, rhi = 0;
+    const uint32_t kmask_lo = (uint32_t)P.kmask, kmask_hi = (uint32_t)(P.kmask >> 32);
+
+    auto roll = [&](uint32_t fw, uint32_t rvlo, uint32_t rvhi) {
+      fhi = __funnelshift_l(flo, fhi, 2) & kmask_hi;  // f = ((f<<2)+code) % 4^K      (:225-229)
+      flo = ((flo << 2) | fw) & kmask_lo;
+      rlo = __funnelshift_r(rlo, rhi, 2) | rvlo;      // r = (r>>2) + (ccode<<(2K-2)) (:233-236)
+      rhi = (rhi >> 2) | rvhi;
+    };
+    auto roll_char = [&](uint32_t c) {
+      const uint2 e = lut[c];
+      if (rc_hi) roll(e.x, 0u, e.y); else roll(e.x, e.y, 0u);
+    };
+    auto emit = [&]() {
+      const uint64_t f = ((uint64_t)fhi << 32) | flo, r = ((uint64_t)rhi << 32) | rlo;
+      const uint64_t canon = f < r ? f : r;                         // :345
+      const uint32_t b = unrevhash64_hi(canon) >> (32 - P.S);       // :347
+      const uint32_t fp = fingerprint(revhash64(canon), P.mask_M, P.maxrem, P.M);  // :346,:348
+      sink.update(b, fp);
+    };
+
+    // ---- warm-up over the K-1 characters before the first k-mer end
+    if (lo == E0) {
+      // record start: str2numstrand + rcb (:340-341).  Case-insensitive; one foreign byte zeroes
+      // the whole seed (B4), which is the same as K-1 'A's on both strands.
+      bool ok = true;
+      for (uint32_t j = 0; j + 1 < K; ++j) ok = ok && (seed_code(bases[lo + j]) < 4);
+      for (uint32_t j = 0; j + 1 < K; ++j) {
+        const uint32_t code = ok ? seed_code(bases[lo + j]) : 0u;
+        const uint64_t rv = (uint64_t)(3u - code) << P.rc_shift;
+        roll(code, (uint32_t)rv, (uint32_t)(rv >> 32));
+      }
+    } else {
+      for (uint32_t j = 0; j + 1 < K; ++j) roll_char(bases[lo + j]);
+    }
+
+    uint64_t pos = lo + K - 1;        // next character to consume; it ends the k-mer starting at pos-K+1
+    const uint64_t end = hi + K - 1;  // one past the last character this thread consumes
+    while (pos < end && (pos & 15)) {
+      roll_char(bases[pos]);
+      emit();
+      ++pos;
+    }
+    if (pos + 16 <= end) {
+      uint4 cur = __ldg(reinterpret_cast<const uint4*>(bases + pos));
+      while (pos + 16 <= end) {
+        const uint64_t nxt = pos + 16;
+        uint4 pre = cur;
+        if (nxt + 16 <= end) pre = __ldg(reinterpret_cast<const uint4*>(bases + nxt));  // prefetch
+        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            roll_char((w[i] >> (8 * j)) & 0xFFu);
+            emit();
+          }
+        }
+        cur = pre;
+        pos = nxt;
+      }
+    }
+    while (pos < end) {
+      roll_char(bases[pos]);
+      emit();
+      ++pos;
+    }
+  }
+
+  if (SMEM) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < P.F; i += NT) {
+      const uint32_t v = ssk[i];
+      if (v != kEmpty) atomicMin(&grow[i], v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Densification (:313-331).  The reference scans cells in index order and lets every non-empty
+// cell i try to copy itself to t = hash_family(v_i, step) % F if that cell is empty.  Within a
+// pass no new value appears, all holders of one value share one target, and the first holder in
+// scan order decides, so a pass is equivalent to: every empty target takes the value of the
+// LOWEST-INDEX cell aiming at it (verified against the reference).  That is an
+// atomicMin of the source index per target: phase A posts 0x80000000|index into empty targets,
+// phase B replaces the winner's index by its value.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kTent = 0x80000000u;
+
+template <bool SMEM, int NT>
+__global__ void __launch_bounds__(NT) densify_kernel(uint32_t* gsk, DevParams P, uint32_t* flags) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ uint32_t s_count;
+  const uint32_t F = P.F, Fmask = F - 1;
+  uint32_t* grow = gsk + (size_t)blockIdx.x * F;
+  uint32_t* sk = SMEM ? smem : grow;
+
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  uint32_t my_empty = 0;
+  for (uint32_t i = threadIdx.x; i < F; i += NT) {
+    const uint32_t v = grow[i];
+    if (SMEM) sk[i] = v;
+    my_empty += (v == kEmpty);
+  }
+  if (my_empty) atomicAdd(&s_count, my_empty);
+  __syncthreads();
+  uint32_t empty = s_count;
+  __syncthreads();
+  if (empty == 0) return;
+  if (empty == F) {  // nothing was sketched (len <= K): callers of the reference drop the entry
+    if (flags && threadIdx.x == 0) flags[blockIdx.x] |= NQ_ENTRY_SKIPPED;
+    return;
+  }
+
+  uint32_t step = 0, idle = 0;
+  // targets repeat with period F in `step`, so F passes without a fill means the reference's
+  // loop would spin forever (seen on entries with 1-2 k-mers); stop and flag instead.
+  while (empty != 0 && idle < F) {
+    if (threadIdx.x == 0) s_count = 0;
+    for (uint32_t i = threadIdx.x; i < F; i += NT) {
+      const uint32_t v = sk[i];
+      if (v < kTent) {
+        const uint32_t t = (family_a(v, Fmask) + step * family_b(v, Fmask)) & Fmask;
+        if (sk[t] >= kTent) atomicMin(&sk[t], kTent | i);
+      }
+    }
+    __syncthreads();
+    uint32_t filled = 0;
+    for (uint32_t i = threadIdx.x; i < F; i += NT) {
+      const uint32_t x = sk[i];
+      if (x >= kTent && x != kEmpty) {
+        sk[i] = sk[x & ~kTent];
+        ++filled;
+      }
+    }
+    if (filled) atomicAdd(&s_count, filled);
+    __syncthreads();
+    const uint32_t got = s_count;
+    __syncthreads();
+    empty -= got;
+    idle = got ? 0 : idle + 1;
+    ++step;
+  }
+  if (SMEM)
+    for (uint32_t i = threadIdx.x; i < F; i += NT) grow[i] = sk[i];
+  if (empty != 0 && flags && threadIdx.x == 0) flags[blockIdx.x] |= NQ_ENTRY_DENSIFY_STALLED;
+}
+
+static DevParams make_dev_params(const nq_params* p) {
+  DevParams d;
+  d.K = p->K; d.S = p->S; d.W = p->W; d.M = p->M; d.F = p->F;
+  d.mask_M = p->mask_M; d.maxrem = p->maxrem; d.range = (uint32_t)p->range;
+  d.kmask = (1ull << (2 * p->K)) - 1;
+  d.rc_shift = 2 * p->K - 2;
+  return d;
+}
+
+}  // namespace nq
+
+using namespace nq;
+
+template <bool SMEM, int NT>
+static int launch_scan(nq_ctx* ctx, const DevParams& P, const uint8_t* d_bases, const uint64_t* d_offsets,
+                       const Span* d_spans, uint64_t nblocks, uint32_t* d_sk) {
+  const size_t smem = 2048 + (SMEM ? (size_t)P.F * 4 : 0);
+  auto kern = sketch_scan_kernel<SMEM, NT>;
+  NQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NqTimer timer(ctx, NQK_SCAN);
+  kern<<<(unsigned)nblocks, NT, smem, ctx->stream>>>(d_bases, d_offsets, d_spans, d_sk, P);
+  NQ_CHECK_LAUNCH(ctx);
+  return NQ_OK;
+}
+
+int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint64_t bases_capacity,
+                     const uint64_t* h_offsets, uint64_t n, int32_t* d_sketches, uint32_t* d_flags) {
+  NQ_TRY(nq_params_check(p));
+  if (n == 0) return NQ_OK;
+  if (n >= (1ull << 31)) return nq_set_error(NQ_ERR_INVALID, "too many entries in one batch: %llu", (unsigned long long)n);
+  if ((reinterpret_cast<uintptr_t>(d_bases) & 15) != 0)
+    return nq_set_error(NQ_ERR_INVALID, "d_bases must be 16-byte aligned");
+  if (bases_capacity < h_offsets[n])
+    return nq_set_error(NQ_ERR_INVALID, "bases_capacity %llu < offsets[n] %llu", (unsigned long long)bases_capacity,
+                        (unsigned long long)h_offsets[n]);
+  const DevParams P = make_dev_params(p);
+  const size_t cells = (size_t)n * P.F;
+  NQ_CUDA(cudaMemsetAsync(d_sketches, 0xFF, cells * sizeof(int32_t), ctx->stream));
+  if (d_flags) NQ_CUDA(cudaMemsetAsync(d_flags, 0, n * sizeof(uint32_t), ctx->stream));
+
+  // spans: slice entries only when there are too few CTAs to fill the machine
+  uint64_t total_k = 0, longest = 0;
+  for (uint64_t e = 0; e < n; ++e) {
+    const uint64_t len = h_offsets[e + 1] - h_offsets[e];
+    if (len > p->K) {
+      total_k += len - p->K;
+      longest = std::max(longest, len - p->K);
+    }
+  }
+  if (total_k == 0) return nq_launch_densify(ctx, p, d_sketches, n, d_flags);
+  uint64_t span_len = (total_k / ((uint64_t)ctx->sm_count * 8) + 1023) & ~1023ull;
+  span_len = std::max<uint64_t>(span_len, 65536);
+  const bool sliced = longest > span_len;
+
+  uint64_t* d_offsets = nullptr;
+  Span* d_spans = nullptr;
+  uint64_t nblocks = n;
+  NQ_TRY(nq_dmalloc(ctx, (void**)&d_offsets, (n + 1) * sizeof(uint64_t)));
+  NQ_CUDA(cudaMemcpyAsync(d_offsets, h_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<Span> spans;
+  if (sliced) {
+    for (uint64_t e = 0; e < n; ++e) {
+      const uint64_t e0 = h_offsets[e], len = h_offsets[e + 1] - e0;
+      if (len <= p->K) continue;
+      const uint64_t nk = len - p->K;
+      const uint64_t parts = (nk + span_len - 1) / span_len;
+      const uint64_t each = ((nk + parts - 1) / parts + 1023) & ~1023ull;
+      for (uint64_t a = 0; a < nk; a += each)
+        spans.push_back(Span{e0 + a, e0 + std::min(nk, a + each), e0, (uint32_t)e, 0});
+    }
+    nblocks = spans.size();
+    NQ_TRY(nq_dmalloc(ctx, (void**)&d_spans, spans.size() * sizeof(Span)));
+    NQ_CUDA(cudaMemcpyAsync(d_spans, spans.data(), spans.size() * sizeof(Span), cudaMemcpyHostToDevice, ctx->stream));
+    NQ_CUDA(cudaStreamSynchronize(ctx->stream));  // `spans` is pageable host memory
+  }
+
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(d_bases);
+  uint32_t* sk = reinterpret_cast<uint32_t*>(d_sketches);
+  const bool fits = 2048 + (size_t)P.F * 4 <= ctx->smem_optin;
+  const bool small = total_k / std::max<uint64_t>(nblocks, 1) < 16384;  // short entries: small CTAs
+  int st;
+  if (fits)
+    st = small ? launch_scan<true, 128>(ctx, P, b, d_offsets, d_spans, nblocks, sk)
+               : launch_scan<true, 1024>(ctx, P, b, d_offsets, d_spans, nblocks, sk);
+  else
+    st = small ? launch_scan<false, 128>(ctx, P, b, d_offsets, d_spans, nblocks, sk)
+               : launch_scan<false, 1024>(ctx, P, b, d_offsets, d_spans, nblocks, sk);
+  nq_dfree(ctx, d_offsets);
+  nq_dfree(ctx, d_spans);
+  NQ_TRY(st);
+  return nq_launch_densify(ctx, p, d_sketches, n, d_flags);
+}
+
+template <bool SMEM, int NT>
+static int launch_densify(nq_ctx* ctx, const DevParams& P, uint32_t* d_sk, uint64_t n, uint32_t* d_flags) {
+  const size_t smem = SMEM ? (size_t)P.F * 4 : 0;
+  auto kern = densify_kernel<SMEM, NT>;
+  NQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NqTimer timer(ctx, NQK_DENSIFY);
+  kern<<<(unsigned)n, NT, smem, ctx->stream>>>(d_sk, P, d_flags);
+  NQ_CHECK_LAUNCH(ctx);
+  return NQ_OK;
+}
+
+int nq_launch_densify(nq_ctx* ctx, const nq_params* p, int32_t* d_sketches, uint64_t n, uint32_t* d_flags) {
+  NQ_TRY(nq_params_check(p));
+  if (n == 0) return NQ_OK;
+  const DevParams P = make_dev_params(p);
+  uint32_t* sk = reinterpret_cast<uint32_t*>(d_sketches);
+  const bool fits = (size_t)P.F * 4 <= ctx->smem_optin;
+  if (P.F <= 1024) return fits ? launch_densify<true, 64>(ctx, P, sk, n, d_flags) : launch_densify<false, 64>(ctx, P, sk, n, d_flags);
+  if (P.F <= 8192) return fits ? launch_densify<true, 256>(ctx, P, sk, n, d_flags) : launch_densify<false, 256>(ctx, P, sk, n, d_flags);
+  return fits ? launch_densify<true, 1024>(ctx, P, sk, n, d_flags) : launch_densify<false, 1024>(ctx, P, sk, n, d_flags);
+}

@@ -1,0 +1,89 @@
+// microbench.cu — measures the primitives the K4a/K2 designs lean on (B200): shared-memory
+// atomicAdd with random addresses, global RED with random addresses in an L2-resident table,
+// __match_any_sync, and shared atomicMin after a filtering read.  Prints ops/s.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+
+__device__ __forceinline__ uint32_t xs(uint32_t& s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
+
+template <bool PACK>
+__global__ void k_smem_atomic(uint32_t words, int iters, uint32_t* sink) {
+  extern __shared__ uint32_t sm[];
+  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) sm[i] = 0;
+  __syncthreads();
+  uint32_t s = blockIdx.x * 7919u + threadIdx.x * 104729u + 1u;
+  for (int i = 0; i < iters; ++i) {
+    const uint32_t r = xs(s);
+    const uint32_t l = r % (PACK ? words * 2 : words);
+    if (PACK) atomicAdd(&sm[l >> 1], 1u << ((l & 1) * 16)); else atomicAdd(&sm[l], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) sink[blockIdx.x] = sm[0];
+}
+
+__global__ void k_red_global(uint32_t* tab, uint32_t words, int iters) {
+  uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 1u;
+  for (int i = 0; i < iters; ++i) atomicAdd(&tab[xs(s) % words], 1u);
+}
+
+__global__ void k_match(int iters, uint32_t* sink) {
+  uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 1u, acc = 0;
+  for (int i = 0; i < iters; ++i) acc += __popc(__match_any_sync(0xFFFFFFFFu, xs(s) & 4095u));
+  if (acc == 0xDEADBEEF) sink[0] = acc;
+}
+
+__global__ void k_smem_min_filtered(uint32_t words, int iters, uint32_t* sink) {
+  extern __shared__ uint32_t sm[];
+  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) sm[i] = 0xFFFFFFFFu;
+  __syncthreads();
+  uint32_t s = blockIdx.x * 7919u + threadIdx.x * 104729u + 1u;
+  for (int i = 0; i < iters; ++i) {
+    const uint32_t b = xs(s) % words, v = xs(s) >> 20;
+    if (v < sm[b]) atomicMin(&sm[b], v);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) sink[blockIdx.x] = sm[0];
+}
+
+template <typename F>
+static float timeit(F f) {
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  f(); cudaDeviceSynchronize();
+  cudaEventRecord(a); f(); cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b); return ms;
+}
+
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  const int sms = p.multiProcessorCount;
+  printf("device %s, %d SMs, smem optin %zu\n", p.name, sms, p.sharedMemPerBlockOptin);
+  uint32_t* sink; cudaMalloc(&sink, 1 << 20);
+  const int iters = 4096;
+  for (int nt : {256, 512, 1024}) {
+    for (uint32_t words : {5000u, 50000u}) {
+      const size_t smem = words * 4;
+      cudaFuncSetAttribute(k_smem_atomic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_smem_atomic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      float ms = timeit([&] { k_smem_atomic<true><<<sms, nt, smem>>>(words, iters, sink); });
+      printf("smem atomicAdd packed16  nt=%4d words=%6u : %8.1f Gops/s\n", nt, words, (double)sms * nt * iters / ms / 1e6);
+      ms = timeit([&] { k_smem_atomic<false><<<sms, nt, smem>>>(words, iters, sink); });
+      printf("smem atomicAdd u32       nt=%4d words=%6u : %8.1f Gops/s\n", nt, words, (double)sms * nt * iters / ms / 1e6);
+    }
+  }
+  {
+    const uint32_t words = 32768; const size_t smem = words * 4;
+    cudaFuncSetAttribute(k_smem_min_filtered, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    float ms = timeit([&] { k_smem_min_filtered<<<sms, 1024, smem>>>(words, iters, sink); });
+    printf("smem filtered atomicMin  nt=1024 words=%6u : %8.1f Gops/s\n", words, (double)sms * 1024 * iters / ms / 1e6);
+  }
+  for (uint32_t words : {5u << 20, 64u << 20}) {  // 20 MB (L2 resident) and 256 MB
+    uint32_t* tab; cudaMalloc(&tab, (size_t)words * 4); cudaMemset(tab, 0, (size_t)words * 4);
+    float ms = timeit([&] { k_red_global<<<sms * 8, 256>>>(tab, words, 1024); });
+    printf("global RED.ADD random    table=%4u MB      : %8.1f Gops/s\n", words >> 18, (double)sms * 8 * 256 * 1024 / ms / 1e6);
+    cudaFree(tab);
+  }
+  float ms = timeit([&] { k_match<<<sms * 8, 256>>>(1024, sink); });
+  printf("__match_any_sync                              : %8.1f G lane-ops/s\n", (double)sms * 8 * 256 * 1024 / ms / 1e6);
+  return 0;
+}
