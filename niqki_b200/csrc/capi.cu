@@ -110,6 +110,7 @@ extern "C" int nq_ctx_create(int device, void* cuda_stream, nq_ctx** out) {
     ctx->own_stream = true;
   }
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
     ctx->sm_count = prop.multiProcessorCount;
@@ -132,6 +133,13 @@ extern "C" int nq_ctx_destroy(nq_ctx* ctx) {
   nq_timing_resolve(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+  for (auto& s : ctx->slot) {
+    cudaFree(s.d_bases); cudaFree(s.d_sk); cudaFree(s.d_flags);
+    if (s.h2d) cudaEventDestroy(s.h2d);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.d2h) cudaEventDestroy(s.d2h);
+  }
   delete ctx;
   return NQ_OK;
 }
@@ -234,55 +242,61 @@ extern "C" int nq_sketch_batch(nq_ctx* ctx, const nq_params* p, const char* base
     cap_entries = std::max(cap_entries, cut[b + 1] - cut[b]);
   }
   cap_bases = (cap_bases + 15 + 16) & ~15ull;
-  struct Slot {
-    char* d_bases = nullptr;
-    int32_t* d_sk = nullptr;
-    uint32_t* d_flags = nullptr;
-    cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
-    std::vector<uint64_t> local_off;
-  } slot[2];
   int st = NQ_OK;
   cudaError_t e = cudaSuccess;
   const int nslots = cut.size() > 2 ? 2 : 1;
-  for (int s = 0; s < nslots && e == cudaSuccess; ++s) {
-    if ((e = cudaMalloc((void**)&slot[s].d_bases, cap_bases)) != cudaSuccess) break;
-    if ((e = cudaMalloc((void**)&slot[s].d_sk, cap_entries * F * 4)) != cudaSuccess) break;
-    if ((e = cudaMalloc((void**)&slot[s].d_flags, cap_entries * 4)) != cudaSuccess) break;
-    cudaEventCreateWithFlags(&slot[s].h2d, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&slot[s].done, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&slot[s].d2h, cudaEventDisableTiming);
+  for (int i = 0; i < nslots && e == cudaSuccess; ++i) {
+    nq_ctx::Slot& s = ctx->slot[i];
+    if (!s.h2d) {
+      cudaEventCreateWithFlags(&s.h2d, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&s.d2h, cudaEventDisableTiming);
+    }
+    if (s.cap_bases < cap_bases) {
+      cudaFree(s.d_bases); s.d_bases = nullptr; s.cap_bases = 0;
+      if ((e = cudaMalloc((void**)&s.d_bases, cap_bases)) != cudaSuccess) break;
+      s.cap_bases = cap_bases;
+    }
+    if (s.cap_cells < cap_entries * F) {
+      cudaFree(s.d_sk); s.d_sk = nullptr; s.cap_cells = 0;
+      if ((e = cudaMalloc((void**)&s.d_sk, cap_entries * F * 4)) != cudaSuccess) break;
+      s.cap_cells = cap_entries * F;
+    }
+    if (s.cap_entries < cap_entries) {
+      cudaFree(s.d_flags); s.d_flags = nullptr; s.cap_entries = 0;
+      if ((e = cudaMalloc((void**)&s.d_flags, cap_entries * 4)) != cudaSuccess) break;
+      s.cap_entries = cap_entries;
+    }
   }
   if (e != cudaSuccess) st = nq_set_error(NQ_ERR_CUDA, "sketch batch allocation failed: %s", cudaGetErrorString(e));
+  std::vector<uint64_t> local_off[2];
   for (size_t b = 0; st == NQ_OK && b + 1 < cut.size(); ++b) {
-    Slot& s = slot[b % nslots];
+    nq_ctx::Slot& s = ctx->slot[b % nslots];
+    std::vector<uint64_t>& loff = local_off[b % nslots];
     const uint64_t e0 = cut[b], e1 = cut[b + 1], nb = e1 - e0, base0 = offsets[e0], nbytes = offsets[e1] - base0;
-    if (b >= (size_t)nslots) cudaEventSynchronize(s.d2h);  // slot's previous results are out
-    s.local_off.resize(nb + 1);
-    for (uint64_t i = 0; i <= nb; ++i) s.local_off[i] = offsets[e0 + i] - base0;
+    if (b >= (size_t)nslots) cudaEventSynchronize(s.d2h);  // the slot's previous results are out
+    loff.resize(nb + 1);
+    for (uint64_t i = 0; i <= nb; ++i) loff[i] = offsets[e0 + i] - base0;
     if (nbytes) e = cudaMemcpyAsync(s.d_bases, bases + base0, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream);
     if (e != cudaSuccess) { st = nq_set_error(NQ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
     cudaEventRecord(s.h2d, ctx->copy_stream);
     cudaStreamWaitEvent(ctx->stream, s.h2d, 0);
-    st = nq_launch_sketch(ctx, p, s.d_bases, cap_bases, s.local_off.data(), nb, s.d_sk, s.d_flags);
+    st = nq_launch_sketch(ctx, p, s.d_bases, s.cap_bases, loff.data(), nb, s.d_sk, s.d_flags);
     if (st != NQ_OK) break;
     cudaEventRecord(s.done, ctx->stream);
-    cudaStreamWaitEvent(ctx->copy_stream, s.done, 0);
-    e = cudaMemcpyAsync(sketches + e0 * F, s.d_sk, nb * F * 4, cudaMemcpyDeviceToHost, ctx->copy_stream);
+    cudaStreamWaitEvent(ctx->d2h_stream, s.done, 0);
+    e = cudaMemcpyAsync(sketches + e0 * F, s.d_sk, nb * F * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
     if (e == cudaSuccess && flags)
-      e = cudaMemcpyAsync(flags + e0, s.d_flags, nb * 4, cudaMemcpyDeviceToHost, ctx->copy_stream);
+      e = cudaMemcpyAsync(flags + e0, s.d_flags, nb * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
     if (e != cudaSuccess) { st = nq_set_error(NQ_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); break; }
-    cudaEventRecord(s.d2h, ctx->copy_stream);
+    cudaEventRecord(s.d2h, ctx->d2h_stream);
   }
   if ((e = cudaStreamSynchronize(ctx->copy_stream)) != cudaSuccess && st == NQ_OK)
     st = nq_set_error(NQ_ERR_CUDA, "sketch batch failed: %s", cudaGetErrorString(e));
+  if ((e = cudaStreamSynchronize(ctx->d2h_stream)) != cudaSuccess && st == NQ_OK)
+    st = nq_set_error(NQ_ERR_CUDA, "sketch batch failed: %s", cudaGetErrorString(e));
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess && st == NQ_OK)
     st = nq_set_error(NQ_ERR_CUDA, "sketch batch failed: %s", cudaGetErrorString(e));
-  for (int s = 0; s < 2; ++s) {
-    cudaFree(slot[s].d_bases); cudaFree(slot[s].d_sk); cudaFree(slot[s].d_flags);
-    if (slot[s].h2d) cudaEventDestroy(slot[s].h2d);
-    if (slot[s].done) cudaEventDestroy(slot[s].done);
-    if (slot[s].d2h) cudaEventDestroy(slot[s].d2h);
-  }
   return st;
 }
 

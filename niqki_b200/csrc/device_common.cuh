@@ -16,6 +16,7 @@ struct DevParams {
   uint32_t range;
   uint64_t kmask;     // 4^K - 1  (min %= offsetUpdatekmer, :228)
   uint32_t rc_shift;  // 2K-2     (:235)
+  uint32_t filter;    // scan kernel: read the cell before the atomicMin
 };
 
 // x = ((x>>32)^x) * C  — one round of the xorshift-multiply mixers (:292-293, :301-302)
@@ -32,11 +33,28 @@ __device__ __forceinline__ uint64_t unrevhash64(uint64_t x) {
   x = fold_mul(fold_mul(x, kUnrevC), kUnrevC);
   return (x >> 32) ^ x;
 }
+// ---- forms used by the scan kernel (same arithmetic, fewer instructions) -----------------------
+// high word of (hi:lo)*(Ch:Cl) only: mulhi(lo,Cl) + lo*Ch + hi*Cl  -> 2 IMAD + 1 IMAD.HI
+__device__ __forceinline__ uint32_t mul64c_hi(uint32_t hi, uint32_t lo, uint32_t Ch, uint32_t Cl) {
+  return __umulhi(lo, Cl) + (lo * Ch + hi * Cl);
+}
 // High 32 bits of unrevhash64(x): the final fold leaves the high word untouched, and the bucket
 // id (:347) only needs `hash >> (64-S)` with S <= 31.
-__device__ __forceinline__ uint32_t unrevhash64_hi(uint64_t x) {
-  x = fold_mul(fold_mul(x, kUnrevC), kUnrevC);
-  return (uint32_t)(x >> 32);
+__device__ __forceinline__ uint32_t unrevhash64_hi32(uint64_t x) {
+  constexpr uint32_t Ch = (uint32_t)(kUnrevC >> 32), Cl = (uint32_t)kUnrevC;
+  x = fold_mul(x, kUnrevC);
+  const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x ^ hi;
+  return mul64c_hi(hi, lo, Ch, Cl);
+}
+// get_fingerprint (:277-287) from the two words of the hash.  With maxrem <= 32 only the high
+// word's leading zeros matter: hi == 0 gives clz >= 32 >= maxrem, i.e. a zero HLL part either way.
+template <bool SMALL_REM>
+__device__ __forceinline__ uint32_t fingerprint32(uint32_t hi, uint32_t lo, uint32_t mask_M, uint32_t maxrem, uint32_t M) {
+  int lz;
+  if (SMALL_REM) lz = __clz((int)hi);
+  else lz = hi ? __clz((int)hi) : 32 + __clz((int)lo);
+  const int rem = max(0, (int)maxrem - lz);
+  return (lo & mask_M) + ((uint32_t)rem << M);
 }
 
 // get_fingerprint (:277-287) with clz64(0) := 64 (bsr on 0 is UB in the reference; observed fp=0)

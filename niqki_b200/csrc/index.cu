@@ -134,10 +134,10 @@ int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketch
     return st;
   };
   cudaError_t e;
-  if ((e = cudaMalloc((void**)&ix->d_row, (size_t)F * (range + 1) * 4)) != cudaSuccess ||
-      (e = cudaMalloc((void**)&ix->d_gids, (size_t)F * n * 4)) != cudaSuccess)
-    return fail(nq_set_error(NQ_ERR_CUDA, "index allocation failed: %s", cudaGetErrorString(e)));
   int st;
+  if ((st = nq_dmalloc(ctx, (void**)&ix->d_row, (size_t)F * (range + 1) * 4)) != NQ_OK ||
+      (st = nq_dmalloc(ctx, (void**)&ix->d_gids, (size_t)F * n * 4)) != NQ_OK)
+    return fail(st);
   if ((st = nq_dmalloc(ctx, (void**)&d_fpT, (size_t)F * n_pad * 2)) != NQ_OK) return fail(st);
   if ((st = nq_dmalloc(ctx, (void**)&d_total, 8)) != NQ_OK) return fail(st);
   if (cudaMemsetAsync(d_total, 0, 8, ctx->stream) != cudaSuccess) return fail(nq_set_error(NQ_ERR_CUDA, "memset failed"));
@@ -174,9 +174,12 @@ int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketch
 
 extern "C" int nq_index_free(nq_index* ix) {
   if (!ix) return NQ_OK;
-  cudaFree(ix->d_row);
-  cudaFree(ix->d_gids);
-  cudaFree(ix->d_pool);
+  if (ix->ctx) {
+    cudaSetDevice(ix->ctx->device);
+    nq_dfree(ix->ctx, ix->d_row);
+    nq_dfree(ix->ctx, ix->d_gids);
+    nq_dfree(ix->ctx, ix->d_pool);
+  }
   delete ix;
   return NQ_OK;
 }
@@ -263,11 +266,12 @@ extern "C" int nq_index_import(nq_ctx* ctx, const nq_params* p, const uint32_t* 
   }
   nq_index* ix = new nq_index();
   ix->ctx = ctx; ix->p = *p; ix->n = n_genomes; ix->gid_base = gid_base; ix->n_stride = stride; ix->n_postings = total;
-  cudaError_t e;
-  if ((e = cudaMalloc((void**)&ix->d_row, hrow.size() * 4)) != cudaSuccess ||
-      (e = cudaMalloc((void**)&ix->d_gids, hg.size() * 4)) != cudaSuccess ||
-      (e = cudaMemcpy(ix->d_row, hrow.data(), hrow.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(ix->d_gids, hg.data(), hg.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+  cudaError_t e = cudaSuccess;
+  if (nq_dmalloc(ctx, (void**)&ix->d_row, hrow.size() * 4) != NQ_OK ||
+      nq_dmalloc(ctx, (void**)&ix->d_gids, hg.size() * 4) != NQ_OK ||
+      (e = cudaMemcpyAsync(ix->d_row, hrow.data(), hrow.size() * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(ix->d_gids, hg.data(), hg.size() * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
     nq_index_free(ix);
     return nq_set_error(NQ_ERR_CUDA, "index import failed: %s", cudaGetErrorString(e));
   }

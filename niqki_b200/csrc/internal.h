@@ -13,7 +13,15 @@ struct nq_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;  // compute stream (owned or borrowed)
   bool own_stream = false;
-  cudaStream_t copy_stream = nullptr;  // H2D / D2H pipeline stream (owned)
+  cudaStream_t copy_stream = nullptr;  // H2D pipeline stream (owned)
+  cudaStream_t d2h_stream = nullptr;   // D2H pipeline stream (owned)
+  // persistent staging of nq_sketch_batch (host-buffer form): two slots, grown on demand
+  struct Slot {
+    char* d_bases = nullptr; size_t cap_bases = 0;
+    int32_t* d_sk = nullptr; size_t cap_cells = 0;
+    uint32_t* d_flags = nullptr; size_t cap_entries = 0;
+    cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
+  } slot[2];
   int sm_count = 148;
   size_t smem_optin = 0;  // max dynamic shared memory per block (opt-in)
   uint64_t launches = 0;  // kernels launched through this context

@@ -181,12 +181,10 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
   unsigned long long total = 0, stats[2] = {0, 0};
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (ix->pool_cap < want) {
-      cudaFree(ix->d_pool);
+      nq_dfree(ctx, ix->d_pool);
       ix->d_pool = nullptr;
       ix->pool_cap = 0;
-      cudaError_t e = cudaMalloc((void**)&ix->d_pool, want * 8);
-      if (e != cudaSuccess) return fail(nq_set_error(NQ_ERR_CUDA, "hit pool allocation (%llu hits) failed: %s",
-                                                     (unsigned long long)want, cudaGetErrorString(e)));
+      if ((st = nq_dmalloc(ctx, (void**)&ix->d_pool, want * 8)) != NQ_OK) return fail(st);
       ix->pool_cap = want;
     }
     a.pool = ix->d_pool; a.pool_cap = ix->pool_cap; a.cursor = d_cursor; a.hit_begin = d_begin; a.hit_n = d_n;

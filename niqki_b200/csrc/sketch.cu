@@ -9,6 +9,7 @@
 // merged into the entry's sketch in HBM with atomicMin — bucket-min is associative and
 // commutative, so slicing is exact (SURVEY.md App. A3 "Chunking").
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "device_common.cuh"
@@ -48,7 +49,12 @@ struct KmerState {
 template <bool SMEM>
 struct SketchSink {
   uint32_t* sk;  // shared (SMEM) or global sketch row
+  bool filter;   // read-before-atomic (dev knob NQ_SCAN_NOFILTER=1 turns it off for the smem sink)
   __device__ __forceinline__ void update(uint32_t b, uint32_t fp) const {
+    if (SMEM && !filter) {
+      atomicMin(&sk[b], fp);
+      return;
+    }
     // sketch[b] = min(sketch[b], fp) with empty = 0xFFFFFFFF (:350-355).  A plain read filters out
     // the ~95% of k-mers that cannot lower the cell; a stale read only makes the filter
     // conservative because cells never increase.
@@ -56,7 +62,7 @@ struct SketchSink {
   }
 };
 
-template <bool SMEM, int NT>
+template <bool SMEM, int NT, bool RC_HI, bool SMALL_REM>
 __global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __restrict__ bases,
                                                          const uint64_t* __restrict__ offsets,
                                                          const Span* __restrict__ spans, uint32_t* gsk,
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __res
   }
   if (A >= B) return;
 
-  const bool rc_hi = P.rc_shift >= 32;
+  constexpr bool rc_hi = RC_HI;  // 2K-2 >= 32: the complement code enters the high word
   for (uint32_t c = threadIdx.x; c < 256; c += NT) {
     const uint32_t rv = rv_code(c);
     lut[c] = make_uint2(fw_code(c), rc_hi ? rv << (P.rc_shift - 32) : rv << P.rc_shift);
@@ -88,7 +94,7 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __res
   if (SMEM)
     for (uint32_t i = threadIdx.x; i < P.F; i += NT) ssk[i] = kEmpty;
   __syncthreads();
-  SketchSink<SMEM> sink{SMEM ? ssk : grow};
+  SketchSink<SMEM> sink{SMEM ? ssk : grow, P.filter != 0};
 
   // this thread's run of k-mer starts [lo, hi): 16-byte aligned slices of the span
   const uint64_t base = A & ~15ull;
@@ -112,12 +118,13 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __res
       const uint2 e = lut[c];
       if (rc_hi) roll(e.x, 0u, e.y); else roll(e.x, e.y, 0u);
     };
+    const uint32_t bshift = 32 - P.S;
     auto emit = [&]() {
       const uint64_t f = ((uint64_t)fhi << 32) | flo, r = ((uint64_t)rhi << 32) | rlo;
-      const uint64_t canon = f < r ? f : r;                         // :345
-      const uint32_t b = unrevhash64_hi(canon) >> (32 - P.S);       // :347
-      const uint32_t fp = fingerprint(revhash64(canon), P.mask_M, P.maxrem, P.M);  // :346,:348
-      sink.update(b, fp);
+      const uint64_t canon = f < r ? f : r;                          // :345
+      const uint32_t b = unrevhash64_hi32(canon) >> bshift;         // :347
+      const uint64_t h = revhash64(canon);                           // :346
+      sink.update(b, fingerprint32<SMALL_REM>((uint32_t)(h >> 32), (uint32_t)h, P.mask_M, P.maxrem, P.M));  // :348
     };
 
     // ---- warm-up over the K-1 characters before the first k-mer end
@@ -254,6 +261,8 @@ static DevParams make_dev_params(const nq_params* p) {
   d.mask_M = p->mask_M; d.maxrem = p->maxrem; d.range = (uint32_t)p->range;
   d.kmask = (1ull << (2 * p->K)) - 1;
   d.rc_shift = 2 * p->K - 2;
+  const char* nf = getenv("NQ_SCAN_NOFILTER");
+  d.filter = (nf && nf[0] == '1') ? 0u : 1u;
   return d;
 }
 
@@ -261,16 +270,26 @@ static DevParams make_dev_params(const nq_params* p) {
 
 using namespace nq;
 
-template <bool SMEM, int NT>
-static int launch_scan(nq_ctx* ctx, const DevParams& P, const uint8_t* d_bases, const uint64_t* d_offsets,
-                       const Span* d_spans, uint64_t nblocks, uint32_t* d_sk) {
+template <bool SMEM, int NT, bool RC_HI, bool SMALL_REM>
+static int launch_scan_t(nq_ctx* ctx, const DevParams& P, const uint8_t* d_bases, const uint64_t* d_offsets,
+                         const Span* d_spans, uint64_t nblocks, uint32_t* d_sk) {
   const size_t smem = 2048 + (SMEM ? (size_t)P.F * 4 : 0);
-  auto kern = sketch_scan_kernel<SMEM, NT>;
+  auto kern = sketch_scan_kernel<SMEM, NT, RC_HI, SMALL_REM>;
   NQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NqTimer timer(ctx, NQK_SCAN);
   kern<<<(unsigned)nblocks, NT, smem, ctx->stream>>>(d_bases, d_offsets, d_spans, d_sk, P);
   NQ_CHECK_LAUNCH(ctx);
   return NQ_OK;
+}
+
+template <bool SMEM, int NT>
+static int launch_scan(nq_ctx* ctx, const DevParams& P, const uint8_t* d_bases, const uint64_t* d_offsets,
+                       const Span* d_spans, uint64_t nblocks, uint32_t* d_sk) {
+  const bool rc_hi = P.rc_shift >= 32, small_rem = P.maxrem <= 32;
+  if (rc_hi) return small_rem ? launch_scan_t<SMEM, NT, true, true>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk)
+                              : launch_scan_t<SMEM, NT, true, false>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk);
+  return small_rem ? launch_scan_t<SMEM, NT, false, true>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk)
+                   : launch_scan_t<SMEM, NT, false, false>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk);
 }
 
 int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint64_t bases_capacity,
