@@ -85,6 +85,11 @@ uint64_t nq_ctx_last_query_gathered(const nq_ctx* ctx);
 /* pinned host memory for fast host<->device copies */
 void* nq_host_alloc(size_t bytes);
 void nq_host_free(void* p);
+/* plain device memory / synchronous copies for hosts that do not link the CUDA runtime
+ * (kind: 0 host->device, 1 device->host, 2 device->device) */
+int nq_device_alloc(nq_ctx* ctx, size_t bytes, void** out);
+int nq_device_free(nq_ctx* ctx, void* p);
+int nq_device_copy(nq_ctx* ctx, void* dst, const void* src, size_t bytes, int kind);
 
 /* ---- sketching: Index::compute_sketch + sketch_densification ---------------------------- */
 /* src/niqki_index.cpp:335-358, 313-331 (and 114-123, 211-236, 240-273, 277-310 underneath).
@@ -94,6 +99,17 @@ void nq_host_free(void* p);
  * `flags` (nullable) receives NQ_ENTRY_* per entry. */
 int nq_sketch_batch(nq_ctx* ctx, const nq_params* p, const char* bases, const uint64_t* offsets,
                     uint64_t n, int32_t* sketches, uint32_t* flags);
+/* Record form.  The reference's whole-file loops (insert_file_whole :442-457, query_file_whole
+ * :505-519) call compute_sketch once per FASTA/FASTQ record on ONE sketch; with more than one
+ * record > K that loop never terminates, so the defined behaviour here is: every
+ * record is scanned with its own seed (:340-341), records of one entry are min-merged, and the
+ * entry is densified once.  `rec_entry[n_records]` (non-decreasing; NULL = one entry per record)
+ * maps records to sketch rows 0..n_entries-1; entries without any record > K come back all -1
+ * with NQ_ENTRY_SKIPPED.  `sketches_on_device` != 0: `sketches` is a device array (flags stay a
+ * host array either way) — the CLI host keeps its sketch store in HBM. */
+int nq_sketch_records(nq_ctx* ctx, const nq_params* p, const char* bases, const uint64_t* rec_offsets,
+                      uint64_t n_records, const uint32_t* rec_entry, uint64_t n_entries, int32_t* sketches,
+                      uint32_t* flags, int sketches_on_device);
 /* Same with the characters already in HBM.  `d_bases` must be 16-byte aligned and its allocation
  * must extend to `bases_capacity` >= offsets[n] rounded up to 16.  `offsets` stays a host array.
  * `d_sketches` / `d_flags` are device buffers (d_flags nullable). */

@@ -51,6 +51,10 @@ SYMBOLS = {
     "nq_host_alloc": (_VP, [C.c_size_t]),
     "nq_host_free": (None, [_VP]),
     "nq_sketch_batch": (C.c_int, [_VP, _P, _VP, _VP, C.c_uint64, _VP, _VP]),
+    "nq_sketch_records": (C.c_int, [_VP, _P, _VP, _VP, C.c_uint64, _VP, C.c_uint64, _VP, _VP, C.c_int]),
+    "nq_device_alloc": (C.c_int, [_VP, C.c_size_t, C.POINTER(_VP)]),
+    "nq_device_free": (C.c_int, [_VP, _VP]),
+    "nq_device_copy": (C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_int]),
     "nq_sketch_batch_device": (C.c_int, [_VP, _P, _VP, C.c_uint64, _VP, C.c_uint64, _VP, _VP]),
     "nq_densify_device": (C.c_int, [_VP, _P, _VP, C.c_uint64, _VP]),
     "nq_index_build": (C.c_int, [_VP, _P, _VP, C.c_uint64, C.c_uint32, C.POINTER(_VP)]),

@@ -203,7 +203,7 @@ extern "C" int nq_sketch_batch_device(nq_ctx* ctx, const nq_params* p, const cha
                                       const uint64_t* offsets, uint64_t n, int32_t* d_sketches, uint32_t* d_flags) {
   if (!ctx || !offsets || (n && (!d_bases || !d_sketches))) return nq_set_error(NQ_ERR_INVALID, "null argument");
   NQ_CUDA(cudaSetDevice(ctx->device));
-  return nq_launch_sketch(ctx, p, d_bases, bases_capacity, offsets, n, d_sketches, d_flags);
+  return nq_launch_sketch(ctx, p, d_bases, bases_capacity, offsets, n, nullptr, n, d_sketches, d_flags);
 }
 
 extern "C" int nq_densify_device(nq_ctx* ctx, const nq_params* p, int32_t* d_sketches, uint64_t n, uint32_t* d_flags) {
@@ -214,31 +214,51 @@ extern "C" int nq_densify_device(nq_ctx* ctx, const nq_params* p, int32_t* d_ske
 
 // Host-buffer form: entries are grouped into device batches; batch i+1's characters are copied
 // (copy stream) while batch i is sketched (compute stream), and batch i's sketches travel back
-// while batch i+1 runs.
-extern "C" int nq_sketch_batch(nq_ctx* ctx, const nq_params* p, const char* bases, const uint64_t* offsets, uint64_t n,
-                               int32_t* sketches, uint32_t* flags) {
-  if (!ctx || !offsets || (n && (!bases || !sketches))) return nq_set_error(NQ_ERR_INVALID, "null argument");
+// (or are placed in the caller's device array) while batch i+1 runs.  `rec_entry` (nullable)
+// maps records to sketch rows, non-decreasing, so an entry's records are contiguous.
+static int sketch_records_impl(nq_ctx* ctx, const nq_params* p, const char* bases, const uint64_t* offsets,
+                               uint64_t n_rec, const uint32_t* rec_entry, uint64_t n_entries, int32_t* sketches,
+                               uint32_t* flags, bool out_on_device) {
+  if (!ctx || !offsets || (n_rec && !bases) || (n_entries && !sketches)) return nq_set_error(NQ_ERR_INVALID, "null argument");
   NQ_TRY(nq_params_check(p));
   NQ_CUDA(cudaSetDevice(ctx->device));
-  if (n == 0) return NQ_OK;
+  if (!rec_entry) n_entries = n_rec;
+  if (n_entries == 0) return NQ_OK;
   const uint64_t F = p->F;
   const uint64_t max_bases = 512ull << 20, max_cells = (1ull << 30) / 4;  // per batch: 512 MB in, 1 GB out
-  // batch boundaries
+  // first record of every entry (entries without records are legal: they stay empty and are flagged)
+  std::vector<uint64_t> first(n_entries + 1, n_rec);
+  if (rec_entry) {
+    uint32_t prev = 0;
+    for (uint64_t r = n_rec; r-- > 0;) {
+      if (rec_entry[r] >= n_entries) return nq_set_error(NQ_ERR_INVALID, "record %llu maps to entry %u >= %llu", (unsigned long long)r, rec_entry[r], (unsigned long long)n_entries);
+      first[rec_entry[r]] = r;
+    }
+    for (uint64_t r = 0; r < n_rec; ++r) {
+      if (rec_entry[r] < prev) return nq_set_error(NQ_ERR_INVALID, "rec_entry must be non-decreasing");
+      prev = rec_entry[r];
+    }
+    for (uint64_t e = n_entries; e-- > 0;)
+      if (first[e] == n_rec || first[e] > first[e + 1]) first[e] = first[e + 1];
+  } else {
+    for (uint64_t e = 0; e <= n_entries; ++e) first[e] = e;
+  }
+  // batch boundaries (in entries)
   std::vector<uint64_t> cut{0};
   {
     uint64_t b0 = 0;
-    for (uint64_t e = 0; e < n; ++e) {
-      const bool full = (offsets[e + 1] - offsets[b0] > max_bases || (e + 1 - b0) * F > max_cells) && e > b0;
+    for (uint64_t e = 0; e < n_entries; ++e) {
+      const bool full = (offsets[first[e + 1]] - offsets[first[b0]] > max_bases || (e + 1 - b0) * F > max_cells) && e > b0;
       if (full) {
         cut.push_back(e);
         b0 = e;
       }
     }
-    cut.push_back(n);
+    cut.push_back(n_entries);
   }
   uint64_t cap_bases = 0, cap_entries = 0;
   for (size_t b = 0; b + 1 < cut.size(); ++b) {
-    cap_bases = std::max(cap_bases, offsets[cut[b + 1]] - offsets[cut[b]]);
+    cap_bases = std::max(cap_bases, offsets[first[cut[b + 1]]] - offsets[first[cut[b]]]);
     cap_entries = std::max(cap_entries, cut[b + 1] - cut[b]);
   }
   cap_bases = (cap_bases + 15 + 16) & ~15ull;
@@ -257,7 +277,7 @@ extern "C" int nq_sketch_batch(nq_ctx* ctx, const nq_params* p, const char* base
       if ((e = cudaMalloc((void**)&s.d_bases, cap_bases)) != cudaSuccess) break;
       s.cap_bases = cap_bases;
     }
-    if (s.cap_cells < cap_entries * F) {
+    if (!out_on_device && s.cap_cells < cap_entries * F) {
       cudaFree(s.d_sk); s.d_sk = nullptr; s.cap_cells = 0;
       if ((e = cudaMalloc((void**)&s.d_sk, cap_entries * F * 4)) != cudaSuccess) break;
       s.cap_cells = cap_entries * F;
@@ -270,22 +290,31 @@ extern "C" int nq_sketch_batch(nq_ctx* ctx, const nq_params* p, const char* base
   }
   if (e != cudaSuccess) st = nq_set_error(NQ_ERR_CUDA, "sketch batch allocation failed: %s", cudaGetErrorString(e));
   std::vector<uint64_t> local_off[2];
+  std::vector<uint32_t> local_ent[2];
   for (size_t b = 0; st == NQ_OK && b + 1 < cut.size(); ++b) {
     nq_ctx::Slot& s = ctx->slot[b % nslots];
     std::vector<uint64_t>& loff = local_off[b % nslots];
-    const uint64_t e0 = cut[b], e1 = cut[b + 1], nb = e1 - e0, base0 = offsets[e0], nbytes = offsets[e1] - base0;
+    std::vector<uint32_t>& lent = local_ent[b % nslots];
+    const uint64_t e0 = cut[b], e1 = cut[b + 1], nb = e1 - e0;
+    const uint64_t r0 = first[e0], r1 = first[e1], nr = r1 - r0, base0 = offsets[r0], nbytes = offsets[r1] - base0;
     if (b >= (size_t)nslots) cudaEventSynchronize(s.d2h);  // the slot's previous results are out
-    loff.resize(nb + 1);
-    for (uint64_t i = 0; i <= nb; ++i) loff[i] = offsets[e0 + i] - base0;
+    loff.resize(nr + 1);
+    for (uint64_t i = 0; i <= nr; ++i) loff[i] = offsets[r0 + i] - base0;
+    if (rec_entry) {
+      lent.resize(nr);
+      for (uint64_t i = 0; i < nr; ++i) lent[i] = rec_entry[r0 + i] - (uint32_t)e0;
+    }
     if (nbytes) e = cudaMemcpyAsync(s.d_bases, bases + base0, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream);
     if (e != cudaSuccess) { st = nq_set_error(NQ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
     cudaEventRecord(s.h2d, ctx->copy_stream);
     cudaStreamWaitEvent(ctx->stream, s.h2d, 0);
-    st = nq_launch_sketch(ctx, p, s.d_bases, s.cap_bases, loff.data(), nb, s.d_sk, s.d_flags);
+    int32_t* d_out = out_on_device ? sketches + e0 * F : s.d_sk;
+    st = nq_launch_sketch(ctx, p, s.d_bases, s.cap_bases, loff.data(), nr, rec_entry ? lent.data() : nullptr, nb, d_out,
+                          s.d_flags);
     if (st != NQ_OK) break;
     cudaEventRecord(s.done, ctx->stream);
     cudaStreamWaitEvent(ctx->d2h_stream, s.done, 0);
-    e = cudaMemcpyAsync(sketches + e0 * F, s.d_sk, nb * F * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+    if (!out_on_device) e = cudaMemcpyAsync(sketches + e0 * F, s.d_sk, nb * F * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
     if (e == cudaSuccess && flags)
       e = cudaMemcpyAsync(flags + e0, s.d_flags, nb * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
     if (e != cudaSuccess) { st = nq_set_error(NQ_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); break; }
@@ -298,6 +327,43 @@ extern "C" int nq_sketch_batch(nq_ctx* ctx, const nq_params* p, const char* base
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess && st == NQ_OK)
     st = nq_set_error(NQ_ERR_CUDA, "sketch batch failed: %s", cudaGetErrorString(e));
   return st;
+}
+
+extern "C" int nq_sketch_batch(nq_ctx* ctx, const nq_params* p, const char* bases, const uint64_t* offsets, uint64_t n,
+                               int32_t* sketches, uint32_t* flags) {
+  return sketch_records_impl(ctx, p, bases, offsets, n, nullptr, n, sketches, flags, false);
+}
+
+extern "C" int nq_sketch_records(nq_ctx* ctx, const nq_params* p, const char* bases, const uint64_t* rec_offsets,
+                                 uint64_t n_records, const uint32_t* rec_entry, uint64_t n_entries, int32_t* sketches,
+                                 uint32_t* flags, int sketches_on_device) {
+  return sketch_records_impl(ctx, p, bases, rec_offsets, n_records, rec_entry, n_entries, sketches, flags,
+                             sketches_on_device != 0);
+}
+
+// ---------------------------------------------------------------- plain device memory for hosts
+// that do not link the CUDA runtime themselves (the C++ CLI host keeps its sketch store in HBM)
+extern "C" int nq_device_alloc(nq_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  NQ_CUDA(cudaSetDevice(ctx->device));
+  NQ_CUDA(cudaMalloc(out, bytes ? bytes : 16));
+  return NQ_OK;
+}
+extern "C" int nq_device_free(nq_ctx* ctx, void* p) {
+  if (!ctx) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  NQ_CUDA(cudaSetDevice(ctx->device));
+  NQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  NQ_CUDA(cudaFree(p));
+  return NQ_OK;
+}
+extern "C" int nq_device_copy(nq_ctx* ctx, void* dst, const void* src, size_t bytes, int kind) {
+  if (!ctx || (bytes && (!dst || !src))) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  if (kind < 0 || kind > 2) return nq_set_error(NQ_ERR_INVALID, "copy kind %d (0 H2D, 1 D2H, 2 D2D)", kind);
+  NQ_CUDA(cudaSetDevice(ctx->device));
+  const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  NQ_CUDA(cudaMemcpyAsync(dst, src, bytes, k, ctx->stream));
+  NQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NQ_OK;
 }
 
 // ---------------------------------------------------------------- index / query / matrix

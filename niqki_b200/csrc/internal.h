@@ -82,7 +82,8 @@ int nq_params_check(const nq_params* p);
 
 // ---- sketch.cu
 int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint64_t bases_capacity,
-                     const uint64_t* h_offsets, uint64_t n, int32_t* d_sketches, uint32_t* d_flags);
+                     const uint64_t* h_offsets, uint64_t n, const uint32_t* h_rec_entry, uint64_t n_entries,
+                     int32_t* d_sketches, uint32_t* d_flags);
 int nq_launch_densify(nq_ctx* ctx, const nq_params* p, int32_t* d_sketches, uint64_t n, uint32_t* d_flags);
 
 // ---- index.cu / query.cu / matrix.cu

@@ -292,20 +292,30 @@ static int launch_scan(nq_ctx* ctx, const DevParams& P, const uint8_t* d_bases, 
                    : launch_scan_t<SMEM, NT, false, false>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk);
 }
 
+// `n` records delimited by h_offsets[n+1]; record i is min-merged into sketch row h_rec_entry[i]
+// (NULL = one entry per record, row i).  Rows are densified once, after every record of the batch
+// has been scanned.
 int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint64_t bases_capacity,
-                     const uint64_t* h_offsets, uint64_t n, int32_t* d_sketches, uint32_t* d_flags) {
+                     const uint64_t* h_offsets, uint64_t n, const uint32_t* h_rec_entry, uint64_t n_entries,
+                     int32_t* d_sketches, uint32_t* d_flags) {
   NQ_TRY(nq_params_check(p));
-  if (n == 0) return NQ_OK;
-  if (n >= (1ull << 31)) return nq_set_error(NQ_ERR_INVALID, "too many entries in one batch: %llu", (unsigned long long)n);
+  if (!h_rec_entry) n_entries = n;
+  if (n_entries == 0) return NQ_OK;
+  if (n >= (1ull << 31) || n_entries >= (1ull << 31))
+    return nq_set_error(NQ_ERR_INVALID, "too many entries in one batch: %llu", (unsigned long long)n);
+  if (h_rec_entry)
+    for (uint64_t e = 0; e < n; ++e)
+      if (h_rec_entry[e] >= n_entries) return nq_set_error(NQ_ERR_INVALID, "record %llu maps to entry %u >= %llu",
+                                                           (unsigned long long)e, h_rec_entry[e], (unsigned long long)n_entries);
   if ((reinterpret_cast<uintptr_t>(d_bases) & 15) != 0)
     return nq_set_error(NQ_ERR_INVALID, "d_bases must be 16-byte aligned");
   if (bases_capacity < h_offsets[n])
     return nq_set_error(NQ_ERR_INVALID, "bases_capacity %llu < offsets[n] %llu", (unsigned long long)bases_capacity,
                         (unsigned long long)h_offsets[n]);
   const DevParams P = make_dev_params(p);
-  const size_t cells = (size_t)n * P.F;
+  const size_t cells = (size_t)n_entries * P.F;
   NQ_CUDA(cudaMemsetAsync(d_sketches, 0xFF, cells * sizeof(int32_t), ctx->stream));
-  if (d_flags) NQ_CUDA(cudaMemsetAsync(d_flags, 0, n * sizeof(uint32_t), ctx->stream));
+  if (d_flags) NQ_CUDA(cudaMemsetAsync(d_flags, 0, n_entries * sizeof(uint32_t), ctx->stream));
 
   // spans: slice entries only when there are too few CTAs to fill the machine
   uint64_t total_k = 0, longest = 0;
@@ -316,10 +326,10 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
       longest = std::max(longest, len - p->K);
     }
   }
-  if (total_k == 0) return nq_launch_densify(ctx, p, d_sketches, n, d_flags);
+  if (total_k == 0) return nq_launch_densify(ctx, p, d_sketches, n_entries, d_flags);
   uint64_t span_len = (total_k / ((uint64_t)ctx->sm_count * 8) + 1023) & ~1023ull;
   span_len = std::max<uint64_t>(span_len, 65536);
-  const bool sliced = longest > span_len;
+  const bool sliced = longest > span_len || h_rec_entry != nullptr;  // a record->row map needs spans
 
   uint64_t* d_offsets = nullptr;
   Span* d_spans = nullptr;
@@ -335,7 +345,7 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
       const uint64_t parts = (nk + span_len - 1) / span_len;
       const uint64_t each = ((nk + parts - 1) / parts + 1023) & ~1023ull;
       for (uint64_t a = 0; a < nk; a += each)
-        spans.push_back(Span{e0 + a, e0 + std::min(nk, a + each), e0, (uint32_t)e, 0});
+        spans.push_back(Span{e0 + a, e0 + std::min(nk, a + each), e0, h_rec_entry ? h_rec_entry[e] : (uint32_t)e, 0});
     }
     nblocks = spans.size();
     NQ_TRY(nq_dmalloc(ctx, (void**)&d_spans, spans.size() * sizeof(Span)));
@@ -357,7 +367,7 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
   nq_dfree(ctx, d_offsets);
   nq_dfree(ctx, d_spans);
   NQ_TRY(st);
-  return nq_launch_densify(ctx, p, d_sketches, n, d_flags);
+  return nq_launch_densify(ctx, p, d_sketches, n_entries, d_flags);
 }
 
 template <bool SMEM, int NT>

@@ -261,11 +261,76 @@ def gen_synth():
     json.dump(out, open(os.path.join(OUT, "synth.json"), "w"), indent=0)
 
 
+def gen_cli_lines():
+    """--indexlines / --querylines / --dump / --load / -G through the reference CLI (1 thread) on a
+    small FASTA and FASTQ with multi-line records, lowercase, N runs and records of length < K,
+    == K and just above K.  Inputs and decompressed outputs are both stored."""
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+
+    def rnd(n):
+        return bytes(rng.choice(acgt, size=n))
+
+    base = [rnd(int(rng.integers(150, 600))) for _ in range(8)]
+    recs = []
+    for i in range(40):
+        s = bytearray(base[i % 8])
+        for _ in range(int(rng.integers(0, 12))):
+            s[int(rng.integers(0, len(s)))] = int(rng.choice(acgt))
+        if i % 7 == 3:
+            s[50:58] = b"NNNNNNNN"
+        if i % 9 == 4:
+            s[5:12] = bytes(s[5:12]).lower()
+        if i % 11 == 5:
+            s[100:104] = b"acgt"
+        recs.append(bytes(s))
+    recs[13] = rnd(20)   # < K: dropped by Biogetline
+    recs[14] = rnd(31)   # == K: dropped by the > K gate
+    recs[15] = rnd(64)
+    fa = b""
+    for i, s in enumerate(recs):
+        fa += b">read%d some description\n" % i
+        w = 70 if i % 2 else 10_000  # multi-line and single-line records
+        fa += b"".join(s[j:j + w] + b"\n" for j in range(0, len(s), w))
+    fq = b"".join(b"@read%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)) for i, s in enumerate(recs))
+    qrecs = [recs[0], recs[9][:120], rnd(200), recs[22]]
+    qfa = b"".join(b">q%d\n%s\n" % (i, s) for i, s in enumerate(qrecs))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    arr = {"reads_fa": np.frombuffer(fa, np.uint8), "reads_fq": np.frombuffer(fq, np.uint8),
+           "queries_fa": np.frombuffer(qfa, np.uint8)}
+    runs = {
+        "fa": ["-i", "reads.fa", "-l", "queries.fa", "-S", "8", "-J", "0.2"],
+        "fq": ["-i", "reads.fq", "-l", "queries.fa", "-S", "8", "-J", "0.2"],
+        "fa_self_J0": ["-i", "reads.fa", "-l", "reads.fa", "-S", "6", "-W", "8", "-K", "21"],
+        "fa_G": ["-i", "reads.fa", "-l", "queries.fa", "-S", "8", "-J", "0.1", "-G", "300"],
+        "fa_dump": ["-i", "reads.fa", "-S", "8", "-J", "0.2", "-D", "dump.gz"],
+        "fa_load": ["-L", "dump.gz", "-l", "queries.fa"],
+    }
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "reads.fa"), "wb").write(fa)
+        open(os.path.join(td, "reads.fq"), "wb").write(fq)
+        open(os.path.join(td, "queries.fa"), "wb").write(qfa)
+        for name, args in runs.items():
+            subprocess.run([REF_CLI] + args + ["-O", f"{name}.gz"], cwd=td, env=env, check=True, timeout=600,
+                           stdout=subprocess.DEVNULL)
+            arr[f"out_{name}"] = np.frombuffer(gzip.open(os.path.join(td, f"{name}.gz"), "rb").read(), np.uint8)
+        dump = gzip.open(os.path.join(td, "dump.gz"), "rb").read()
+        arr["dump_md5"] = np.array(hashlib.md5(dump).hexdigest())
+        arr["dump_len"] = np.array(len(dump))
+    arr["runs"] = np.array(json.dumps(runs))
+    np.savez_compressed(os.path.join(OUT, "cli_lines.npz"), **arr)
+    print("cli_lines:", {k: int(v.size) for k, v in arr.items() if k.startswith("out_")})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "cli_lines":
+        gen_cli_lines()
+        sys.exit(0)
     rng = np.random.default_rng(20261017)
     gen_scalars(rng)
     gen_sketches(rng)
     gen_small_index(rng)
     gen_synth()
     gen_c1()
+    gen_cli_lines()
     print("golden fixtures written to", OUT)

@@ -1,0 +1,6 @@
+#!/bin/bash
+# CLI + regression run
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q --timeout 900 > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -30 gpurun_out/pytest_gpu.log
