@@ -1,0 +1,121 @@
+"""Multi-GPU host logic of the NIQKI path: one process per GPU, index sharded by genome id.
+
+SURVEY.md §8e: the path shards naturally.  Rank r owns the contiguous gid block
+``[r*ceil(N/G), (r+1)*ceil(N/G))`` — it sketches those genomes and builds its own CSR, no
+communication.  Queries: every rank sketches its slice of the query entries, ONE all-gather of the
+query sketches (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests), every rank
+counts all queries against its shard; per-shard hit lists are disjoint in gid, so the merge on
+rank 0 is concatenate + sort by (count, gid) descending — exactly the order
+``Index::query_sketch`` produces (/root/reference/src/niqki_index.cpp:685).  Thresholding is per
+genome, so it commutes with sharding.
+
+The compute object (``engine``) is anything with the ``niqki_b200.Index`` methods used here
+(``compute_sketches`` / ``sketch_many``, ``insert_sketches``, ``query_sketches``); the product
+passes a ``niqki_b200.Index`` (CUDA), the CPU tests pass an adapter.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_total: int, world: int, rank: int):
+    """Contiguous block of ids owned by ``rank``: gpu = gid // ceil(N/G)."""
+    per = -(-n_total // world) if n_total else 0
+    lo = min(n_total, rank * per)
+    return lo, min(n_total, lo + per)
+
+
+def owner_of(gid: int, n_total: int, world: int) -> int:
+    per = -(-n_total // world)
+    return gid // per
+
+
+def merge_hit_lists(parts, nq: int):
+    """``parts`` = per-shard ``(ptr u64[nq+1], counts u32[], gids u32[])``.  Returns the merged
+    triple with every query's hits sorted by (count, gid) descending (std::greater<pair>, :685)."""
+    ptr = np.zeros(nq + 1, np.uint64)
+    keys = []
+    for q in range(nq):
+        segs = []
+        for p, c, g in parts:
+            a, b = int(p[q]), int(p[q + 1])
+            if b > a:
+                segs.append((c[a:b].astype(np.uint64) << np.uint64(32)) | g[a:b].astype(np.uint64))
+        k = np.sort(np.concatenate(segs))[::-1] if segs else np.zeros(0, np.uint64)
+        keys.append(k)
+        ptr[q + 1] = ptr[q] + np.uint64(k.size)
+    allk = np.concatenate(keys) if keys else np.zeros(0, np.uint64)
+    return ptr, (allk >> np.uint64(32)).astype(np.uint32), (allk & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+
+class ShardedIndex:
+    """One rank's view of a gid-sharded index.  ``dist`` is ``torch.distributed`` (initialised by
+    the caller) or ``None`` for a single process."""
+
+    def __init__(self, engine, dist=None, device=None):
+        self.engine = engine
+        self.dist = dist if (dist is not None and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.device = device
+        self.n_total = 0
+
+    # ---- index phase: no communication
+    def index_entries(self, n_total: int, load_entries):
+        """``load_entries(lo, hi)`` returns this rank's entries (list of byte arrays) for gids
+        [lo, hi).  Builds the shard with global gids."""
+        self.n_total = n_total
+        lo, hi = shard_range(n_total, self.world, self.rank)
+        self.gid_lo, self.gid_hi = lo, hi
+        if hi > lo:
+            sk, _ = self.engine.sketch_many(load_entries(lo, hi))
+            self.engine.insert_sketches(sk, gid_base=lo)
+        return lo, hi
+
+    # ---- query phase: one all-gather of sketches, then local counting, then a gather of hits
+    def allgather_sketches(self, local):
+        """``local`` int32 [n_local][F] (numpy or torch) -> all ranks' sketches in rank order."""
+        if not self.dist:
+            return local
+        import torch
+
+        t = torch.as_tensor(local)
+        if self.device is not None:
+            t = t.to(self.device)
+        F = t.shape[1] if t.ndim == 2 else self.engine.F
+        counts = torch.zeros(self.world, dtype=torch.int64, device=t.device)
+        mine = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        self.dist.all_gather_into_tensor(counts, mine)
+        cmax = int(counts.max().item())
+        padded = torch.full((cmax, F), -1, dtype=torch.int32, device=t.device)
+        padded[: t.shape[0]] = t
+        out = torch.empty((self.world * cmax, F), dtype=torch.int32, device=t.device)
+        self.dist.all_gather_into_tensor(out, padded)
+        keep = [out[r * cmax: r * cmax + int(counts[r].item())] for r in range(self.world)]
+        return torch.cat(keep, dim=0)
+
+    def query_entries(self, nq_total: int, load_queries, min_score=None):
+        """Every rank sketches queries [lo,hi) of its slice, all-gathers, counts against its shard.
+        Returns the merged ``(ptr, counts, gids)`` on rank 0 (``None`` elsewhere)."""
+        lo, hi = shard_range(nq_total, self.world, self.rank)
+        if hi > lo:
+            local, _ = self.engine.sketch_many(load_queries(lo, hi))
+        else:
+            local = np.zeros((0, self.engine.F), np.int32)
+        allsk = self.allgather_sketches(local)
+        if self.dist and self.device is None:
+            allsk = allsk.numpy()
+        if self.gid_hi > self.gid_lo:
+            part = self.engine.query_sketches(allsk, min_score)
+        else:
+            part = (np.zeros(nq_total + 1, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint32))
+        return self.gather_and_merge(part, nq_total)
+
+    def gather_and_merge(self, part, nq: int):
+        if not self.dist:
+            return merge_hit_lists([part], nq)
+        parts = [None] * self.world if self.rank == 0 else None
+        self.dist.gather_object(tuple(np.asarray(x) for x in part), parts, dst=0)
+        if self.rank != 0:
+            return None
+        return merge_hit_lists(parts, nq)
