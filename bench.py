@@ -32,6 +32,7 @@ SEED = 42
 GENOME_LEN = 5_000_000
 K, S, W, H, J = 31, 15, 12, 4, 0.1
 RATES = (0.001, 0.01, 0.05)
+OPS_PER_BASE = 38  # algorithmic int32 ops per base of the sketch scan
 METRIC = "Gbases/s sketched (index 10k x 5 Mbp genomes + query 1k mutated copies, per GPU shard)"
 
 
@@ -369,11 +370,23 @@ def main():
         scan_ms, scan_n = kt["scan"]
         q_ms, q_n = kt["query"]
         bases_per_scan = (G + Q) * L * args.steps / max(scan_n, 1)
-        scan_gbs = bases_per_scan / (scan_ms / max(scan_n, 1) / 1e3) / 1e9 if scan_ms else None
+        scan_s = scan_ms / max(scan_n, 1) / 1e3
+        scan_gbases = bases_per_scan / scan_s / 1e9 if scan_ms else None
         nq_total = Q * world
-        q_bytes = 4 * gathered + nq_total * F * (8 + 4)  # + 8 B per hit (negligible at minjac 0.1)
+        q_bytes = 4 * gathered + nq_total * F * (8 + 2)  # gids + row pairs + u16 sketch (+ 8 B/hit, negligible)
         q_gbs = q_bytes / (q_ms / max(q_n, 1) / 1e3) / 1e9 if q_ms else None
-        sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+        sm_clk = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        int_peak = 148 * 128 * sm_clk * 1e6 / 1e12  # Tint32-op/s: 148 SMs x 128 lanes x sampled SM clock
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except (OSError, ValueError):
+            pass
+
+        def ncu_traffic(kernel):
+            t = traffic.get(kernel)
+            return t["dram_bytes_per_launch"] if t and t.get("genomes_per_gpu") == G and t.get("queries") == nq_total else None
+
         line = {
             "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -385,17 +398,24 @@ def main():
             "query_sketches_per_s": nq_total / (q_ms / max(q_n, 1) / 1e3) if q_ms else None,
             "index_postings": info["n_postings"],
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt.items()},
-            "roofline": {"kernel": "sketch_scan_kernel", "bound": "hbm", "achieved": scan_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": (scan_gbs / hbm_peak) if scan_gbs else None, "traffic": None,
-                         "peak_source": peak_src,
-                         "note": "1 B/base algorithmic; the kernel is integer-ALU bound (see roofline_alu)"},
-            "roofline_alu": {"kernel": "sketch_scan_kernel", "bound": "int32 issue", "unit": "Gbases/s",
-                             "achieved": scan_gbs,
-                             "peak": 148 * 4 * sm_clk * 1e6 * 32 / 57 / 1e9,
-                             "note": "peak = 148 SMs x 4 schedulers x 1 warp-instr/clk at the sampled SM clock / 57 SASS instr per base"},
+            # dominant kernel (>90% of the step): integer-ALU bound, DESIGN.md 4 / SURVEY 8d
+            "roofline": {"kernel": "sketch_scan_kernel", "bound": "int32-alu",
+                         "achieved": scan_gbases * OPS_PER_BASE / 1e3 if scan_gbases else None, "peak": int_peak,
+                         "unit": "Tint32-op/s", "frac": (scan_gbases * OPS_PER_BASE / 1e3 / int_peak) if scan_gbases else None,
+                         "traffic": ncu_traffic("sketch_scan_kernel"),
+                         "algorithmic_ops_per_base": OPS_PER_BASE, "gbases_per_s": scan_gbases,
+                         "launches": int(scan_n), "ms_per_launch": scan_ms / max(scan_n, 1),
+                         "peak_source": "148 SMs x 128 int32 lanes x SM clock sampled during the run (no measured INT32 "
+                                        "figure in MEASURED_PEAKS.json; SURVEY 8d fallback)",
+                         "hbm": {"achieved": scan_gbases, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": scan_gbases / hbm_peak if scan_gbases else None,
+                                 "note": "1 B/base algorithmic: this kernel is not HBM-bound"}},
+            # the HBM-bound kernel of the path (north_star target >= 0.5)
             "roofline_query": {"kernel": "query_count_kernel", "bound": "hbm", "achieved": q_gbs, "peak": hbm_peak,
-                               "unit": "GB/s", "frac": (q_gbs / hbm_peak) if q_gbs else None, "traffic": None,
-                               "algorithmic_bytes": q_bytes, "gathered_postings": gathered},
+                               "unit": "GB/s", "frac": (q_gbs / hbm_peak) if q_gbs else None,
+                               "traffic": ncu_traffic("query_count_kernel"), "peak_source": peak_src,
+                               "algorithmic_bytes": q_bytes, "gathered_postings": gathered,
+                               "launches": int(q_n), "ms_per_launch": q_ms / max(q_n, 1)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "first_hits": first_hits,
         }
         if not args.no_cpu_baseline and world == 1:
