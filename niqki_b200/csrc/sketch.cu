@@ -49,27 +49,47 @@ struct KmerState {
 template <bool SMEM>
 struct SketchSink {
   uint32_t* sk;  // shared (SMEM) or global sketch row
-  bool filter;   // read-before-atomic (dev knob NQ_SCAN_NOFILTER=1 turns it off for the smem sink)
   __device__ __forceinline__ void update(uint32_t b, uint32_t fp) const {
-    if (SMEM && !filter) {
+    // sketch[b] = min(sketch[b], fp) with empty = 0xFFFFFFFF (:350-355).
+    if (SMEM) {
+      // shared memory: a fire-and-forget ATOMS.MIN per k-mer is cheaper than read + compare +
+      // conditional atomic (measured on B200: 563 vs 517 Gbases/s)
       atomicMin(&sk[b], fp);
-      return;
+    } else {
+      // global memory: a plain read filters out the ~95% of k-mers that cannot lower the cell; a
+      // stale read only makes the filter conservative because cells never increase
+      if (fp < sk[b]) atomicMin(&sk[b], fp);
     }
-    // sketch[b] = min(sketch[b], fp) with empty = 0xFFFFFFFF (:350-355).  A plain read filters out
-    // the ~95% of k-mers that cannot lower the cell; a stale read only makes the filter
-    // conservative because cells never increase.
-    if (fp < sk[b]) atomicMin(&sk[b], fp);
   }
 };
 
-template <bool SMEM, int NT, bool RC_HI, bool SMALL_REM>
+// (hi:lo) * (Ch:Cl) mod 2^64 as a chain of three multiply-adds with 32-bit addends (IMAD.WIDE,
+// IMAD, IMAD): no zeroed register pair, no separate add.  PTX pins the association.
+__device__ __forceinline__ uint2 mul64c(uint32_t hi, uint32_t lo, uint32_t Ch, uint32_t Cl) {
+  uint32_t plo, phi;
+  asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(plo), "=r"(phi) : "r"(lo), "r"(Cl));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(phi) : "r"(lo), "r"(Ch));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(phi) : "r"(hi), "r"(Cl));
+  return make_uint2(plo, phi);
+}
+// high word only: IMAD.HI, IMAD, IMAD
+__device__ __forceinline__ uint32_t mul64c_hi_chain(uint32_t hi, uint32_t lo, uint32_t Ch, uint32_t Cl) {
+  uint32_t r;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(lo), "r"(Cl));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r) : "r"(lo), "r"(Ch));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r) : "r"(hi), "r"(Cl));
+  return r;
+}
+
+// DEF = the default parameter set K=31, W=12, H=4 (M=8, mask_M=255, maxrem=15): masks and shifts
+// become immediates (kmask_lo = 2^32-1 needs no AND at all).  S stays a run-time value.
+template <bool SMEM, int NT, bool RC_HI, bool SMALL_REM, bool DEF>
 __global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __restrict__ bases,
                                                          const uint64_t* __restrict__ offsets,
                                                          const Span* __restrict__ spans, uint32_t* gsk,
                                                          DevParams P) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  uint2* lut = reinterpret_cast<uint2*>(smem);  // [256] {fw, rv << (rc_shift or rc_shift-32)}
-  uint32_t* ssk = smem + 512;                   // [F] when SMEM
+  __shared__ uint2 lut[256];                       // {fw, rv << (rc_shift or rc_shift-32)}; static => immediate address
+  extern __shared__ __align__(16) uint32_t ssk[];  // [F] when SMEM
 
   uint64_t A, B, E0;
   uint32_t entry;
@@ -85,16 +105,17 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __res
   }
   if (A >= B) return;
 
-  constexpr bool rc_hi = RC_HI;  // 2K-2 >= 32: the complement code enters the high word
+  constexpr bool rc_hi = RC_HI || DEF;  // 2K-2 >= 32: the complement code enters the high word
+  const uint32_t rc_shift = DEF ? 60u : P.rc_shift;
   for (uint32_t c = threadIdx.x; c < 256; c += NT) {
     const uint32_t rv = rv_code(c);
-    lut[c] = make_uint2(fw_code(c), rc_hi ? rv << (P.rc_shift - 32) : rv << P.rc_shift);
+    lut[c] = make_uint2(fw_code(c), rc_hi ? rv << (rc_shift - 32) : rv << rc_shift);
   }
   uint32_t* grow = gsk + (size_t)entry * P.F;
   if (SMEM)
     for (uint32_t i = threadIdx.x; i < P.F; i += NT) ssk[i] = kEmpty;
   __syncthreads();
-  SketchSink<SMEM> sink{SMEM ? ssk : grow, P.filter != 0};
+  SketchSink<SMEM> sink{SMEM ? ssk : grow};
 
   // this thread's run of k-mer starts [lo, hi): 16-byte aligned slices of the span
   const uint64_t base = A & ~15ull;
@@ -104,13 +125,14 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __res
   const uint64_t hi = min(B, base + (uint64_t)(threadIdx.x + 1) * R);
 
   if (lo < hi) {
-    const uint32_t K = P.K;
+    const uint32_t K = DEF ? 31u : P.K;
     uint32_t flo = 0, fhi = 0, rlo = 0, rhi = 0;
-    const uint32_t kmask_lo = (uint32_t)P.kmask, kmask_hi = (uint32_t)(P.kmask >> 32);
+    const uint32_t kmask_lo = DEF ? 0xFFFFFFFFu : (uint32_t)P.kmask;
+    const uint32_t kmask_hi = DEF ? 0x3FFFFFFFu : (uint32_t)(P.kmask >> 32);
 
     auto roll = [&](uint32_t fw, uint32_t rvlo, uint32_t rvhi) {
       fhi = __funnelshift_l(flo, fhi, 2) & kmask_hi;  // f = ((f<<2)+code) % 4^K      (:225-229)
-      flo = ((flo << 2) | fw) & kmask_lo;
+      flo = DEF ? flo * 4u + fw : ((flo << 2) | fw) & kmask_lo;
       rlo = __funnelshift_r(rlo, rhi, 2) | rvlo;      // r = (r>>2) + (ccode<<(2K-2)) (:233-236)
       rhi = (rhi >> 2) | rvhi;
     };
@@ -119,12 +141,31 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __res
       if (rc_hi) roll(e.x, 0u, e.y); else roll(e.x, e.y, 0u);
     };
     const uint32_t bshift = 32 - P.S;
+    const uint32_t mask_M = DEF ? 255u : P.mask_M, maxrem = DEF ? 15u : P.maxrem, M = DEF ? 8u : P.M;
     auto emit = [&]() {
-      const uint64_t f = ((uint64_t)fhi << 32) | flo, r = ((uint64_t)rhi << 32) | rlo;
-      const uint64_t canon = f < r ? f : r;                          // :345
-      const uint32_t b = unrevhash64_hi32(canon) >> bshift;         // :347
-      const uint64_t h = revhash64(canon);                           // :346
-      sink.update(b, fingerprint32<SMALL_REM>((uint32_t)(h >> 32), (uint32_t)h, P.mask_M, P.maxrem, P.M));  // :348
+      constexpr uint32_t RCh = (uint32_t)(kRevC >> 32), RCl = (uint32_t)kRevC;
+      constexpr uint32_t UCh = (uint32_t)(kUnrevC >> 32), UCl = (uint32_t)kUnrevC;
+      const bool f_lt = (((uint64_t)fhi << 32) | flo) < (((uint64_t)rhi << 32) | rlo);  // canon = min(f, r) (:345)
+      const uint32_t chi = f_lt ? fhi : rhi, clo = f_lt ? flo : rlo;
+      const uint32_t t = clo ^ chi;                              // first fold, shared by both hashes
+      // bucket = unrevhash64(canon) >> (64-S): only the high word of the second product (:347)
+      const uint2 u1 = mul64c(chi, t, UCh, UCl);
+      const uint32_t b = mul64c_hi_chain(u1.y, u1.x ^ u1.y, UCh, UCl) >> bshift;
+      // fingerprint of revhash64(canon) (:346, :277-287): h = (hi2, lo2 ^ hi2)
+      const uint2 r1 = mul64c(chi, t, RCh, RCl);
+      const uint32_t t3 = r1.x ^ r1.y;
+      const uint32_t hh = mul64c_hi_chain(r1.y, t3, RCh, RCl), hl = (t3 * RCl) ^ hh;
+      if (DEF) {
+        // rem = max(0, 15 - clz(hh)) = max(0, bfind(hh) - 16); bfind(0) = -1     (:280-286)
+        // The shared sketch holds fp + 4096 (= max(bfind,16) << 8 instead of max(bfind-16,0) << 8:
+        // a monotone offset, so the minimum is the same cell); the offset comes off at the flush.
+        int msb;
+        asm("bfind.u32 %0, %1;" : "=r"(msb) : "r"(hh));
+        if (SMEM) sink.update(b, (hl & 255u) + ((uint32_t)max(msb, 16) << 8));
+        else sink.update(b, (hl & 255u) + ((uint32_t)max(msb - 16, 0) << 8));
+      } else {
+        sink.update(b, fingerprint32<SMALL_REM>(hh, hl, mask_M, maxrem, M));  // :348
+      }
     };
 
     // ---- warm-up over the K-1 characters before the first k-mer end
@@ -135,7 +176,7 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __res
       for (uint32_t j = 0; j + 1 < K; ++j) ok = ok && (seed_code(bases[lo + j]) < 4);
       for (uint32_t j = 0; j + 1 < K; ++j) {
         const uint32_t code = ok ? seed_code(bases[lo + j]) : 0u;
-        const uint64_t rv = (uint64_t)(3u - code) << P.rc_shift;
+        const uint64_t rv = (uint64_t)(3u - code) << rc_shift;
         roll(code, (uint32_t)rv, (uint32_t)(rv >> 32));
       }
     } else {
@@ -179,7 +220,7 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __res
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < P.F; i += NT) {
       const uint32_t v = ssk[i];
-      if (v != kEmpty) atomicMin(&grow[i], v);
+      if (v != kEmpty) atomicMin(&grow[i], DEF ? v - 4096u : v);
     }
   }
 }
@@ -261,8 +302,7 @@ static DevParams make_dev_params(const nq_params* p) {
   d.mask_M = p->mask_M; d.maxrem = p->maxrem; d.range = (uint32_t)p->range;
   d.kmask = (1ull << (2 * p->K)) - 1;
   d.rc_shift = 2 * p->K - 2;
-  const char* nf = getenv("NQ_SCAN_NOFILTER");
-  d.filter = (nf && nf[0] == '1') ? 0u : 1u;
+  d.filter = 0;
   return d;
 }
 
@@ -270,11 +310,11 @@ static DevParams make_dev_params(const nq_params* p) {
 
 using namespace nq;
 
-template <bool SMEM, int NT, bool RC_HI, bool SMALL_REM>
+template <bool SMEM, int NT, bool RC_HI, bool SMALL_REM, bool DEF>
 static int launch_scan_t(nq_ctx* ctx, const DevParams& P, const uint8_t* d_bases, const uint64_t* d_offsets,
                          const Span* d_spans, uint64_t nblocks, uint32_t* d_sk) {
-  const size_t smem = 2048 + (SMEM ? (size_t)P.F * 4 : 0);
-  auto kern = sketch_scan_kernel<SMEM, NT, RC_HI, SMALL_REM>;
+  const size_t smem = SMEM ? (size_t)P.F * 4 : 0;
+  auto kern = sketch_scan_kernel<SMEM, NT, RC_HI, SMALL_REM, DEF>;
   NQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NqTimer timer(ctx, NQK_SCAN);
   kern<<<(unsigned)nblocks, NT, smem, ctx->stream>>>(d_bases, d_offsets, d_spans, d_sk, P);
@@ -286,15 +326,14 @@ template <bool SMEM, int NT>
 static int launch_scan(nq_ctx* ctx, const DevParams& P, const uint8_t* d_bases, const uint64_t* d_offsets,
                        const Span* d_spans, uint64_t nblocks, uint32_t* d_sk) {
   const bool rc_hi = P.rc_shift >= 32, small_rem = P.maxrem <= 32;
-  if (rc_hi) return small_rem ? launch_scan_t<SMEM, NT, true, true>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk)
-                              : launch_scan_t<SMEM, NT, true, false>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk);
-  return small_rem ? launch_scan_t<SMEM, NT, false, true>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk)
-                   : launch_scan_t<SMEM, NT, false, false>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk);
+  if (P.K == 31 && P.M == 8 && P.mask_M == 255 && P.maxrem == 15)  // the default K/W/H (any S)
+    return launch_scan_t<SMEM, NT, true, true, true>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk);
+  if (rc_hi) return small_rem ? launch_scan_t<SMEM, NT, true, true, false>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk)
+                              : launch_scan_t<SMEM, NT, true, false, false>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk);
+  return small_rem ? launch_scan_t<SMEM, NT, false, true, false>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk)
+                   : launch_scan_t<SMEM, NT, false, false, false>(ctx, P, d_bases, d_offsets, d_spans, nblocks, d_sk);
 }
 
-// `n` records delimited by h_offsets[n+1]; record i is min-merged into sketch row h_rec_entry[i]
-// (NULL = one entry per record, row i).  Rows are densified once, after every record of the batch
-// has been scanned.
 int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint64_t bases_capacity,
                      const uint64_t* h_offsets, uint64_t n, const uint32_t* h_rec_entry, uint64_t n_entries,
                      int32_t* d_sketches, uint32_t* d_flags) {
@@ -355,7 +394,7 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
 
   const uint8_t* b = reinterpret_cast<const uint8_t*>(d_bases);
   uint32_t* sk = reinterpret_cast<uint32_t*>(d_sketches);
-  const bool fits = 2048 + (size_t)P.F * 4 <= ctx->smem_optin;
+  const bool fits = 2048 + 1024 + (size_t)P.F * 4 <= ctx->smem_optin;  // + static LUT + driver reserve
   const bool small = total_k / std::max<uint64_t>(nblocks, 1) < 16384;  // short entries: small CTAs
   int st;
   if (fits)
