@@ -92,12 +92,15 @@ struct nq_index {
   nq_params p{};
   uint32_t n = 0;         // genomes in this shard
   uint32_t gid_base = 0;  // gid of local genome 0
-  uint32_t n_stride = 0;  // slots per cell in d_gids
   uint64_t n_postings = 0;
-  // CSR with a fixed cell stride: list (cell, fp) = d_gids[cell*n_stride + row[cell*(range+1)+fp] ..
-  //                                                          row[cell*(range+1)+fp+1])
-  uint32_t* d_row = nullptr;   // [F][range+1]
-  uint32_t* d_gids = nullptr;  // [F][n_stride], global gids
+  // Cell-major CSR with fixed strides, element type u16 when n <= 65535 ("compact", halves the
+  // bytes every probe drags through L2/HBM), u32 otherwise.  Postings hold LOCAL ids (gid-gid_base).
+  //   {b,e} = dir[cell*row_stride + fp];  list (cell, fp) = gids[cell*gid_stride + b .. + e)
+  uint32_t elem = 4;        // bytes per offset / gid element: 2 or 4
+  uint32_t row_stride = 0;  // directory entries per cell (= range)
+  uint32_t gid_stride = 0;  // elements per cell in d_gids: n rounded up to 32 bytes
+  void* d_row = nullptr;    // directory [F][row_stride] of packed {begin,end}: u32 (elem 2) or uint2 (elem 4)
+  void* d_gids = nullptr;   // [F][gid_stride]
   // device-resident results of the last nq_query_batch_device(out == NULL)
   uint64_t* d_pool = nullptr;
   uint64_t pool_cap = 0;

@@ -12,12 +12,27 @@
 
 namespace nq {
 
+template <typename IT>
+__device__ __forceinline__ void load_dir_entry(const void* dir, size_t at, uint32_t& b, uint32_t& e);
+template <>
+__device__ __forceinline__ void load_dir_entry<uint16_t>(const void* dir, size_t at, uint32_t& b, uint32_t& e) {
+  const uint32_t w = static_cast<const uint32_t*>(dir)[at];
+  b = w & 0xFFFFu;
+  e = w >> 16;
+}
+template <>
+__device__ __forceinline__ void load_dir_entry<uint32_t>(const void* dir, size_t at, uint32_t& b, uint32_t& e) {
+  const uint2 w = static_cast<const uint2*>(dir)[at];
+  b = w.x;
+  e = w.y;
+}
+
 // One warp walks 32 consecutive lists of one cell at a time; non-empty lists are then expanded by
 // the whole warp: rows (members inside [rb,re)) sequentially, columns across lanes.
-__global__ void __launch_bounds__(256) matrix_count_kernel(const uint32_t* __restrict__ row,
-                                                           const uint32_t* __restrict__ gids, uint32_t F,
-                                                           uint32_t range, uint32_t n, uint32_t n_stride,
-                                                           uint32_t gid_base, uint32_t rb, uint32_t re,
+template <typename IT>
+__global__ void __launch_bounds__(256) matrix_count_kernel(const void* __restrict__ dir, const IT* __restrict__ gids,
+                                                           uint32_t F, uint32_t range, uint32_t n, uint32_t row_stride,
+                                                           uint32_t gid_stride, uint32_t rb, uint32_t re,
                                                            uint32_t* __restrict__ counts) {
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -27,23 +42,19 @@ __global__ void __launch_bounds__(256) matrix_count_kernel(const uint32_t* __res
   for (uint64_t grp = warp; grp < ngroups; grp += nwarps) {
     const uint32_t cell = (uint32_t)(grp / groups_per_cell);
     const uint32_t fp = (uint32_t)(grp % groups_per_cell) * 32 + lane;
-    const uint32_t* r = row + (size_t)cell * (range + 1);
     uint32_t b = 0, e = 0;
-    if (fp < range) {
-      b = r[fp];
-      e = r[fp + 1];
-    }
+    if (fp < range) load_dir_entry<IT>(dir, (size_t)cell * row_stride + fp, b, e);
     unsigned live = __ballot_sync(0xFFFFFFFFu, e > b);
-    const uint32_t* g = gids + (size_t)cell * n_stride;
+    const IT* g = gids + (size_t)cell * gid_stride;
     while (live) {
       const int src = __ffs(live) - 1;
       live &= live - 1;
       const uint32_t lb = __shfl_sync(0xFFFFFFFFu, b, src), le = __shfl_sync(0xFFFFFFFFu, e, src);
       for (uint32_t i = lb; i < le; ++i) {
-        const uint32_t a = g[i] - gid_base;
+        const uint32_t a = g[i];
         if (a < rb || a >= re) continue;
         uint32_t* crow = counts + (size_t)(a - rb) * n;
-        for (uint32_t j = lb + lane; j < le; j += 32) atomicAdd(&crow[g[j] - gid_base], 1u);
+        for (uint32_t j = lb + lane; j < le; j += 32) atomicAdd(&crow[g[j]], 1u);
       }
     }
   }
@@ -74,8 +85,14 @@ int nq_matrix_impl(nq_index* ix, uint32_t row_begin, uint32_t row_end, int wrap1
     const size_t cells = (size_t)(re - rb) * n;
     NQ_CUDA(cudaMemsetAsync(d_counts, 0, cells * 4, ctx->stream));
     NqTimer timer(ctx, NQK_MATRIX);
-    matrix_count_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ix->d_row, ix->d_gids, ix->p.F, (uint32_t)ix->p.range, n,
-                                                                     ix->n_stride, ix->gid_base, rb, re, d_counts);
+    if (ix->elem == 2)
+      matrix_count_kernel<uint16_t><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+          ix->d_row, static_cast<const uint16_t*>(ix->d_gids), ix->p.F, (uint32_t)ix->p.range, n, ix->row_stride,
+          ix->gid_stride, rb, re, d_counts);
+    else
+      matrix_count_kernel<uint32_t><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+          ix->d_row, static_cast<const uint32_t*>(ix->d_gids), ix->p.F, (uint32_t)ix->p.range, n, ix->row_stride,
+          ix->gid_stride, rb, re, d_counts);
     NQ_CHECK_LAUNCH(ctx);
     if (wrap16) {
       wrap16_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_counts, cells);

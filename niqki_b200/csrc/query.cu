@@ -1,13 +1,24 @@
 // query.cu — K4a: posting-list gather + per-genome hit counting + fused min_score threshold and
 // compaction.  Replaces Index::query_sketch (/root/reference/src/niqki_index.cpp:633-687).
 //
-// One CTA per query sketch.  The per-genome counters of the shard live in shared memory (two
-// 16-bit counters per word when S <= 15, because a count can never exceed F = 2^S <= 32768 — the
-// same widths the reference uses, :635-683), every thread probes a strided subset of the F
-// cells: row[cell][fp] / row[cell][fp+1] delimit the list, whose gids are gathered and counted
-// with shared-memory atomics.  The threshold pass then compacts (count, gid) pairs in gid order
-// into a global pool (one atomicAdd per query reserves the segment).  Sorting by (count, gid)
-// descending (:685) is done by the host when it merges shards.
+// One CTA per query sketch; all queries of a batch are resident at once where shared memory allows
+// (256-thread CTAs, 8 per SM), so the wave sweeps the cells roughly in step and a cell's directory
+// and lists are served from L2 after their first touch.  The per-genome counters of the shard live
+// in shared memory (two 16-bit counters per word when S <= 15, because a count can never exceed
+// F = 2^S <= 32768 — the same widths the reference uses, :635-683).
+//
+// The gather is bound by the L1TEX tag stage (one cache line per cycle per SM for divergent
+// loads), not by bytes, so it is organised to touch as few (line, instruction) pairs as possible:
+// a warp takes 32 consecutive cells, every lane reads its cell's fingerprint (coalesced) and ONE
+// packed directory word {begin,end}; the 32 lists are then treated as one concatenated stream
+// that the whole warp walks 32 postings at a time — lanes reading neighbouring postings of one list
+// share a cache line, no lane idles on a short list, and every shared-memory atomicAdd carries 32
+// useful lanes.  The owner of stream slot s is found without a search: the lanes whose list starts
+// inside the current 32-slot round set one bit each (REDUX.OR), and a population count of the
+// bits at or below a slot gives the owner's rank among the non-empty lists.
+// The threshold pass then compacts (count, gid) pairs in gid order into a global pool (one
+// atomicAdd per query reserves the segment).  Sorting by (count, gid) descending (:685) is done by
+// the host when it merges shards.
 #include <algorithm>
 #include <vector>
 
@@ -17,10 +28,10 @@
 namespace nq {
 
 struct QueryArgs {
-  const int32_t* qsk;    // [nq][F]
-  const uint32_t* row;   // [F][range+1]
-  const uint32_t* gids;  // [F][n_stride]
-  uint32_t F, range, n, n_stride, gid_base, min_score, wrap_mask;
+  const int32_t* qsk;  // [nq][F]
+  const void* dir;     // [F][row_stride] packed {begin,end} (u16 pair in a u32, or uint2)
+  const void* gids;    // [F][gid_stride] local ids (u16 or u32)
+  uint32_t F, range, n, row_stride, gid_stride, gid_base, min_score, wrap_mask;
   uint64_t* pool;  // count<<32 | gid
   uint64_t pool_cap;
   unsigned long long* cursor;  // [0] pool cursor, [1] posting entries gathered (statistics)
@@ -31,9 +42,26 @@ struct QueryArgs {
 
 enum CountMode { kPack16 = 0, kSmem32 = 1, kGlobal32 = 2 };
 
-template <int MODE, int NT>
+template <typename IT>
+__device__ __forceinline__ void load_dir(const void* dir, size_t at, uint32_t& b, uint32_t& e);
+template <>
+__device__ __forceinline__ void load_dir<uint16_t>(const void* dir, size_t at, uint32_t& b, uint32_t& e) {
+  const uint32_t w = __ldg(static_cast<const uint32_t*>(dir) + at);
+  b = w & 0xFFFFu;
+  e = w >> 16;
+}
+template <>
+__device__ __forceinline__ void load_dir<uint32_t>(const void* dir, size_t at, uint32_t& b, uint32_t& e) {
+  const uint2 w = __ldg(static_cast<const uint2*>(dir) + at);
+  b = w.x;
+  e = w.y;
+}
+
+// IDX = uint32_t when every posting index F*gid_stride fits 32 bits (always for S <= 15 in the compact form)
+template <typename IT, int MODE, int NT, typename IDX>
 __global__ void __launch_bounds__(NT) query_count_kernel(QueryArgs a, uint64_t q0) {
   extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ IDX s_src[NT / 32][32];  // per warp: stream base of the rank-th non-empty list
   __shared__ uint32_t s_warp[NT / 32];
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_total;
@@ -41,28 +69,77 @@ __global__ void __launch_bounds__(NT) query_count_kernel(QueryArgs a, uint64_t q
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t* cnt = MODE == kGlobal32 ? a.gcounts + (size_t)blockIdx.x * a.n : smem;
   const uint32_t words = MODE == kPack16 ? (a.n + 1) / 2 : a.n;
+  constexpr unsigned kFull = 0xFFFFFFFFu;
 
   for (uint32_t i = tid; i < words; i += NT) cnt[i] = 0;
   __syncthreads();
 
   // ---- gather + count (:654-660)
   const int32_t* sk = a.qsk + q * a.F;
+  const IT* gids = static_cast<const IT*>(a.gids);
+  const unsigned le = 0xFFFFFFFFu >> (31 - lane);  // bits at or below this lane
   uint32_t gathered = 0;
-  for (uint32_t cell = tid; cell < a.F; cell += NT) {
-    const uint32_t fp = (uint32_t)sk[cell];
-    if (fp < a.range) {  // 0 <= fp < fingerprint_range (:655)
-      const uint32_t* r = a.row + (size_t)cell * (a.range + 1) + fp;
-      const uint32_t b = r[0], e = r[1];
-      const uint32_t* g = a.gids + (size_t)cell * a.n_stride;
-      gathered += e - b;
-      for (uint32_t j = b; j < e; ++j) {
-        const uint32_t l = g[j] - a.gid_base;
-        if (MODE == kPack16)
-          atomicAdd(&cnt[l >> 1], 1u << ((l & 1) * 16));
-        else
-          atomicAdd(&cnt[l], 1u);
-      }
+  auto count = [&](uint32_t l) {
+    if (MODE == kPack16)
+      atomicAdd(&cnt[l >> 1], (l & 1) ? 0x10000u : 1u);
+    else
+      atomicAdd(&cnt[l], 1u);
+  };
+  // software pipeline over the warp's groups of 32 cells: fingerprints are fetched two groups
+  // ahead, directory words one group ahead, so neither latency sits in front of the stream walk
+  const uint32_t step = NT;
+  uint32_t c_cur = warp * 32;
+  uint32_t fp_next = 0xFFFFFFFFu, fp_next2 = 0xFFFFFFFFu;
+  if (c_cur + step + lane < a.F) fp_next = (uint32_t)__ldg(&sk[c_cur + step + lane]);
+  uint32_t b = 0, e = 0;
+  if (c_cur + lane < a.F) {
+    const uint32_t fp = (uint32_t)__ldg(&sk[c_cur + lane]);
+    if (fp < a.range) load_dir<IT>(a.dir, (size_t)(c_cur + lane) * a.row_stride + fp, b, e);  // 0 <= fp < range (:655)
+  }
+  for (; c_cur < a.F; c_cur += step) {
+    const uint32_t cell = c_cur + lane;
+    // prefetch: fingerprint of group +2, directory word of group +1
+    fp_next2 = 0xFFFFFFFFu;
+    if (c_cur + 2 * step + lane < a.F) fp_next2 = (uint32_t)__ldg(&sk[c_cur + 2 * step + lane]);
+    uint32_t nb = 0, ne = 0;
+    if (fp_next < a.range) load_dir<IT>(a.dir, (size_t)(cell + step) * a.row_stride + fp_next, nb, ne);
+
+    const uint32_t len = e - b;
+    uint32_t incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d) incl += t;
     }
+    const uint32_t excl = incl - len;
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    const unsigned nonempty = __ballot_sync(kFull, len != 0);
+    if (len) s_src[warp][__popc(nonempty & (le >> 1))] = (IDX)((IDX)cell * a.gid_stride + b - excl);
+    __syncwarp();
+    gathered += len;
+    uint32_t starts_before = 0;
+    constexpr int R = 4;  // rounds of 32 postings whose loads are in flight together
+    for (uint32_t r0 = 0; r0 < total; r0 += 32 * R) {
+      uint32_t l[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const uint32_t rel = excl - (r0 + 32 * k);  // wraps to a huge value when the list starts before this round
+        const unsigned m = __reduce_or_sync(kFull, (len && rel < 32u) ? 1u << rel : 0u);
+        const uint32_t s = r0 + 32 * k + lane;
+        l[k] = 0xFFFFFFFFu;
+        if (s < total) {
+          const uint32_t owner = starts_before + __popc(m & le) - 1;
+          l[k] = gids[s_src[warp][owner] + s];
+        }
+        starts_before += __popc(m);
+      }
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if (l[k] != 0xFFFFFFFFu) count(l[k]);
+    }
+    __syncwarp();
+    b = nb; e = ne;
+    fp_next = fp_next2;
   }
   __syncthreads();
 
@@ -79,8 +156,8 @@ __global__ void __launch_bounds__(NT) query_count_kernel(QueryArgs a, uint64_t q
   for (uint32_t g = tid; g < a.n; g += NT) mine += count_of(g) >= a.min_score;
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
-    mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
-    gathered += __shfl_xor_sync(0xFFFFFFFFu, gathered, d);
+    mine += __shfl_xor_sync(kFull, mine, d);
+    gathered += __shfl_xor_sync(kFull, gathered, d);
   }
   if (lane == 0) {
     s_warp[warp] = mine;
@@ -109,7 +186,7 @@ __global__ void __launch_bounds__(NT) query_count_kernel(QueryArgs a, uint64_t q
       c = count_of(g);
       hit = c >= a.min_score;
     }
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+    const unsigned bal = __ballot_sync(kFull, hit);
     __syncthreads();  // s_warp reuse
     if (lane == 0) s_warp[warp] = __popc(bal);
     __syncthreads();
@@ -128,6 +205,34 @@ __global__ void __launch_bounds__(NT) query_count_kernel(QueryArgs a, uint64_t q
 
 using namespace nq;
 
+template <typename IT, int MODE, int NT>
+static cudaError_t launch_query_t(size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st) {
+  const bool idx32 = (uint64_t)a.F * a.gid_stride < (1ull << 32);
+  cudaError_t e;
+  if (idx32) {
+    e = cudaFuncSetAttribute(query_count_kernel<IT, MODE, NT, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    query_count_kernel<IT, MODE, NT, uint32_t><<<nb, NT, smem, st>>>(a, q0);
+  } else {
+    e = cudaFuncSetAttribute(query_count_kernel<IT, MODE, NT, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    query_count_kernel<IT, MODE, NT, uint64_t><<<nb, NT, smem, st>>>(a, q0);
+  }
+  return cudaSuccess;
+}
+template <typename IT>
+static cudaError_t launch_query_it(int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st) {
+  // small counter arrays: 256-thread CTAs so that 8 queries share an SM; large ones: one big CTA
+  const bool small = smem <= 24 * 1024;
+  if (mode == kPack16) return small ? launch_query_t<IT, kPack16, 256>(smem, nb, a, q0, st) : launch_query_t<IT, kPack16, 1024>(smem, nb, a, q0, st);
+  if (mode == kSmem32) return small ? launch_query_t<IT, kSmem32, 256>(smem, nb, a, q0, st) : launch_query_t<IT, kSmem32, 1024>(smem, nb, a, q0, st);
+  return launch_query_t<IT, kGlobal32, 512>(0, nb, a, q0, st);
+}
+static cudaError_t launch_query(uint32_t elem, int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0,
+                                cudaStream_t st) {
+  return elem == 2 ? launch_query_it<uint16_t>(mode, smem, nb, a, q0, st) : launch_query_it<uint32_t>(mode, smem, nb, a, q0, st);
+}
+
 int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t min_score, nq_hits** out) {
   if (!ix) return nq_set_error(NQ_ERR_INVALID, "null index");
   nq_ctx* ctx = ix->ctx;
@@ -139,10 +244,10 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
     return NQ_OK;
   }
   const nq_params& p = ix->p;
-  constexpr int NT = 512;
   QueryArgs a{};
-  a.qsk = d_sketches; a.row = ix->d_row; a.gids = ix->d_gids;
-  a.F = p.F; a.range = (uint32_t)p.range; a.n = ix->n; a.n_stride = ix->n_stride; a.gid_base = ix->gid_base;
+  a.qsk = d_sketches; a.dir = ix->d_row; a.gids = ix->d_gids;
+  a.F = p.F; a.range = (uint32_t)p.range; a.n = ix->n; a.row_stride = ix->row_stride; a.gid_stride = ix->gid_stride;
+  a.gid_base = ix->gid_base;
   a.min_score = min_score;
   a.wrap_mask = p.S <= 7 ? 0xFFu : p.S <= 15 ? 0xFFFFu : 0xFFFFFFFFu;  // counter widths of :635/:651/:667
 
@@ -193,16 +298,8 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
     NqTimer* timer = new NqTimer(ctx, NQK_QUERY);
     for (uint64_t q0 = 0; q0 < nq; q0 += q_per_launch) {
       const unsigned nb = (unsigned)std::min<uint64_t>(q_per_launch, nq - q0);
-      cudaError_t e = cudaSuccess;
-      if (mode == kPack16) {
-        e = cudaFuncSetAttribute(query_count_kernel<kPack16, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        query_count_kernel<kPack16, NT><<<nb, NT, smem, ctx->stream>>>(a, q0);
-      } else if (mode == kSmem32) {
-        e = cudaFuncSetAttribute(query_count_kernel<kSmem32, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        query_count_kernel<kSmem32, NT><<<nb, NT, smem, ctx->stream>>>(a, q0);
-      } else {
-        query_count_kernel<kGlobal32, NT><<<nb, NT, 0, ctx->stream>>>(a, q0);
-      }
+      const cudaError_t e0 = launch_query(ix->elem, mode, smem, nb, a, q0, ctx->stream);
+      cudaError_t e = e0;
       ctx->launches++;
       if (e != cudaSuccess || (e = cudaPeekAtLastError()) != cudaSuccess) {
         delete timer;

@@ -16,8 +16,8 @@ try:
 except Exception as e:
     print("bench failed", e); print(open("gpurun_out/bench_iter.err").read()[-2000:])
 PY
-if [ -n "$NCU_KERNEL" ]; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$NCU_KERNEL -s 1 -c 1 -o gpurun_out/prof_$NCU_KERNEL -f \
-    python bench.py ${NCU_BENCH_ARGS:---genomes 1024 --queries 128 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline} > gpurun_out/ncu_$NCU_KERNEL.out 2>&1
-  tail -2 gpurun_out/ncu_$NCU_KERNEL.out
-fi
+for KN in $NCU_KERNEL; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KN -s 1 -c 1 -o gpurun_out/prof_$KN -f \
+    python bench.py ${NCU_BENCH_ARGS:---genomes 1024 --queries 128 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline} > gpurun_out/ncu_$KN.out 2>&1
+  tail -2 gpurun_out/ncu_$KN.out
+done
