@@ -189,7 +189,7 @@ static cudaError_t launch_cell_sort(nq_ctx* ctx, const uint16_t* d_fpT, uint32_t
 }
 
 static void set_layout(nq_index* ix) {
-  ix->elem = ix->n <= 65535u ? 2u : 4u;
+  ix->elem = ix->n <= kMaxCompact ? 2u : 4u;
   const uint32_t per32 = 32 / ix->elem;
   ix->row_stride = (uint32_t)ix->p.range;  // directory entries per cell (2*elem bytes each)
   ix->gid_stride = (std::max<uint32_t>(ix->n, 1) + per32 - 1) / per32 * per32;
@@ -219,7 +219,7 @@ int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketch
   cudaError_t e;
   int st;
   if ((st = nq_dmalloc(ctx, &ix->d_row, (size_t)F * ix->row_stride * ix->elem * 2)) != NQ_OK ||
-      (st = nq_dmalloc(ctx, &ix->d_gids, (size_t)F * ix->gid_stride * ix->elem)) != NQ_OK)
+      (st = nq_dmalloc(ctx, &ix->d_gids, ((size_t)F * ix->gid_stride + kQuerySlack) * ix->elem)) != NQ_OK)
     return fail(st);
   if ((st = nq_dmalloc(ctx, (void**)&d_fpT, (size_t)F * n_pad * 2)) != NQ_OK) return fail(st);
   if ((st = nq_dmalloc(ctx, (void**)&d_total, 8)) != NQ_OK) return fail(st);
@@ -242,6 +242,8 @@ int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketch
   ix->n_postings = total;
   nq_dfree(ctx, d_fpT);
   nq_dfree(ctx, d_total);
+  d_fpT = nullptr; d_total = nullptr;
+  if ((st = nq_query_prepare(ix)) != NQ_OK) return fail(st);
   *out = ix;
   return NQ_OK;
 }
@@ -343,12 +345,12 @@ static int import_t(nq_index* ix, const uint32_t* list_sizes, const uint32_t* gi
   ix->n_postings = total;
   cudaError_t e = cudaSuccess;
   if (nq_dmalloc(ctx, &ix->d_row, hrow.size() * sizeof(DT)) != NQ_OK ||
-      nq_dmalloc(ctx, &ix->d_gids, hg.size() * sizeof(IT)) != NQ_OK ||
+      nq_dmalloc(ctx, &ix->d_gids, (hg.size() + kQuerySlack) * sizeof(IT)) != NQ_OK ||
       (e = cudaMemcpyAsync(ix->d_row, hrow.data(), hrow.size() * sizeof(DT), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
       (e = cudaMemcpyAsync(ix->d_gids, hg.data(), hg.size() * sizeof(IT), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
       (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
     return nq_set_error(NQ_ERR_CUDA, "index import failed: %s", cudaGetErrorString(e));
-  return NQ_OK;
+  return nq_query_prepare(ix);
 }
 
 extern "C" int nq_index_import(nq_ctx* ctx, const nq_params* p, const uint32_t* list_sizes, const uint32_t* gids,

@@ -20,6 +20,8 @@
 // atomicAdd per query reserves the segment).  Sorting by (count, gid) descending (:685) is done by
 // the host when it merges shards.
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "device_common.cuh"
@@ -42,24 +44,95 @@ struct QueryArgs {
 
 enum CountMode { kPack16 = 0, kSmem32 = 1, kGlobal32 = 2 };
 
+// id carried by stream slots past the end of a group's stream: lands in spare counter word `lane`
+// (shared-memory modes) or is skipped (global mode).  Must fit IT: n <= kMaxCompact in the u16 form.
 template <typename IT>
-__device__ __forceinline__ void load_dir(const void* dir, size_t at, uint32_t& b, uint32_t& e);
-template <>
-__device__ __forceinline__ void load_dir<uint16_t>(const void* dir, size_t at, uint32_t& b, uint32_t& e) {
-  const uint32_t w = __ldg(static_cast<const uint32_t*>(dir) + at);
-  b = w & 0xFFFFu;
-  e = w >> 16;
+__host__ __device__ __forceinline__ uint32_t query_dummy_id(int mode, uint32_t words, uint32_t lane) {
+  return mode == kPack16 ? 2 * (words + lane) : mode == kSmem32 ? words + lane : (uint32_t)(IT)0xFFFFFFFFu;
 }
+
+// Every load of the gather loop is UNCONDITIONAL (dead lanes read a harmless location and their
+// result is neutralised where it is consumed, one loop iteration later): ptxas implements a
+// predicated load as load-to-temporary + predicated MOV right behind it, which stalls the warp
+// for the full memory latency and defeats the software pipeline.
+// Directory word of list (cell, fp): {begin,end} as two u16 in a u32 (compact form) or a uint2.
+// Kept RAW in registers until the group is processed, one loop iteration after the load.
+template <typename IT>
+struct DirWord;
 template <>
-__device__ __forceinline__ void load_dir<uint32_t>(const void* dir, size_t at, uint32_t& b, uint32_t& e) {
-  const uint2 w = __ldg(static_cast<const uint2*>(dir) + at);
-  b = w.x;
-  e = w.y;
+struct DirWord<uint16_t> {
+  uint32_t w;
+  __device__ __forceinline__ void clear() { w = 0; }
+  __device__ __forceinline__ void load(const void* dir, size_t at) { w = __ldg(static_cast<const uint32_t*>(dir) + at); }
+  __device__ __forceinline__ uint32_t begin() const { return w & 0xFFFFu; }
+  __device__ __forceinline__ uint32_t end() const { return w >> 16; }
+};
+template <>
+struct DirWord<uint32_t> {
+  uint32_t x, y;
+  __device__ __forceinline__ void clear() { x = y = 0; }
+  __device__ __forceinline__ void load(const void* dir, size_t at) {
+    const uint2 v = __ldg(static_cast<const uint2*>(dir) + at);
+    x = v.x; y = v.y;
+  }
+  __device__ __forceinline__ uint32_t begin() const { return x; }
+  __device__ __forceinline__ uint32_t end() const { return y; }
+};
+
+// clamped shift: PTX shl.b32 yields 0 for shift amounts >= 32 (C++ leaves that undefined)
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t s) {
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
+  return r;
+}
+// `if (s < total) red.shared.add(addr, v)` as ONE predicated instruction (no branch, no reconvergence)
+__device__ __forceinline__ void red_shared_add_if_lt(uint32_t saddr, uint32_t v, uint32_t s, uint32_t total) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t@q red.shared.add.u32 [%0], %1;\n\t}"
+               :: "r"(saddr), "r"(v), "r"(s), "r"(total) : "memory");
+}
+// Pull a contiguous region into L2 through the bulk-copy engine (no LSU/L1TEX work, no registers).
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+
+// The co-resident query CTAs sweep the cells roughly in step, so each one pulls ITS slice of the
+// directory rows and posting arrays of a chunk of cells two chunks ahead of where it is: DRAM then
+// sees long sequential bursts (the whole index is read about once per launch) and the random
+// probes of every query hit L2.  Purely a hint: a late slice only costs its readers an L2 miss.
+constexpr uint32_t kPfCells = 256;  // cells per prefetch chunk
+constexpr uint32_t kPfAhead = 2;    // chunks of lead
+
+struct PfSlice {  // this lane's piece of every chunk of the two regions: offset inside the chunk, bytes, chunk pitch
+  uint32_t off[2], len[2], pitch[2];
+};
+__device__ __forceinline__ PfSlice make_pf_slice(const QueryArgs& a, uint32_t elem, uint32_t lane) {
+  PfSlice p;
+  const uint32_t cells = min(kPfCells, a.F);
+  const uint32_t cell_bytes[2] = {a.row_stride * 2 * elem, a.gid_stride * elem};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const uint32_t size = cells * cell_bytes[r];  // <= 256 cells * 512 KB
+    p.pitch[r] = size;
+    // the CTA's slice, cut into <= 32 pieces of >= 2 KB (one bulk request per lane)
+    const uint32_t per_cta = ((size + gridDim.x - 1) / gridDim.x + 15) & ~15u;
+    const uint32_t lo = blockIdx.x * per_cta;
+    const uint32_t mine = lo < size ? min(per_cta, size - lo) : 0;
+    const uint32_t piece = max(2048u, ((mine + 31) / 32 + 15) & ~15u);
+    const uint32_t o = lane * piece;
+    p.off[r] = lo + o;
+    p.len[r] = o < mine ? (min(piece, mine - o) + 15) & ~15u : 0;
+  }
+  return p;
+}
+__device__ __forceinline__ void prefetch_chunk(const QueryArgs& a, const PfSlice& p, uint32_t chunk) {
+  if (chunk * kPfCells >= a.F) return;
+  if (p.len[0]) l2_prefetch_bulk(static_cast<const char*>(a.dir) + (size_t)chunk * p.pitch[0] + p.off[0], p.len[0]);
+  if (p.len[1]) l2_prefetch_bulk(static_cast<const char*>(a.gids) + (size_t)chunk * p.pitch[1] + p.off[1], p.len[1]);
 }
 
 // IDX = uint32_t when every posting index F*gid_stride fits 32 bits (always for S <= 15 in the compact form)
-template <typename IT, int MODE, int NT, typename IDX>
-__global__ void __launch_bounds__(NT) query_count_kernel(QueryArgs a, uint64_t q0) {
+template <typename IT, int MODE, int NT, typename IDX, int R = 4, int D = 2>
+__global__ void __launch_bounds__(NT, NT == 128 ? 9 : 1) query_count_kernel(QueryArgs a, uint64_t q0) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ IDX s_src[NT / 32][32];  // per warp: stream base of the rank-th non-empty list
   __shared__ uint32_t s_warp[NT / 32];
@@ -71,6 +144,11 @@ __global__ void __launch_bounds__(NT) query_count_kernel(QueryArgs a, uint64_t q
   const uint32_t words = MODE == kPack16 ? (a.n + 1) / 2 : a.n;
   constexpr unsigned kFull = 0xFFFFFFFFu;
 
+  PfSlice pf{};
+  if (warp == 0) {
+    pf = make_pf_slice(a, sizeof(IT), lane);
+    for (uint32_t ch = 0; ch < kPfAhead; ++ch) prefetch_chunk(a, pf, ch);
+  }
   for (uint32_t i = tid; i < words; i += NT) cnt[i] = 0;
   __syncthreads();
 
@@ -79,11 +157,17 @@ __global__ void __launch_bounds__(NT) query_count_kernel(QueryArgs a, uint64_t q
   const IT* gids = static_cast<const IT*>(a.gids);
   const unsigned le = 0xFFFFFFFFu >> (31 - lane);  // bits at or below this lane
   uint32_t gathered = 0;
+  // count one gathered posting l (stream slot s of `total`)
+  // Slots past the end of the stream (last round of a group only) carry a per-lane dummy id that
+  // lands in 32 spare words behind the counters, so the shared-memory path needs no branch.
+  // (the same ids sit in the 32 elements behind the posting arrays, nq_query_prepare, so that a
+  // dead lane's gather is an ordinary load)
+  const uint32_t dummy = query_dummy_id<IT>(MODE, words, lane);
+  const IDX dead_at = (IDX)a.F * a.gid_stride + lane;
   auto count = [&](uint32_t l) {
-    if (MODE == kPack16)
-      atomicAdd(&cnt[l >> 1], (l & 1) ? 0x10000u : 1u);
-    else
-      atomicAdd(&cnt[l], 1u);
+    if (MODE == kPack16) atomicAdd(&smem[l >> 1], (l & 1) * 0xFFFFu + 1u);
+    else if (MODE == kSmem32) atomicAdd(&smem[l], 1u);
+    else if (l != dummy) atomicAdd(&cnt[l], 1u);  // dummy = all ones in IT, never a local id
   };
   // software pipeline over the warp's groups of 32 cells: fingerprints are fetched two groups
   // ahead, directory words one group ahead, so neither latency sits in front of the stream walk
@@ -91,20 +175,41 @@ __global__ void __launch_bounds__(NT) query_count_kernel(QueryArgs a, uint64_t q
   uint32_t c_cur = warp * 32;
   uint32_t fp_next = 0xFFFFFFFFu, fp_next2 = 0xFFFFFFFFu;
   if (c_cur + step + lane < a.F) fp_next = (uint32_t)__ldg(&sk[c_cur + step + lane]);
-  uint32_t b = 0, e = 0;
-  if (c_cur + lane < a.F) {
-    const uint32_t fp = (uint32_t)__ldg(&sk[c_cur + lane]);
-    if (fp < a.range) load_dir<IT>(a.dir, (size_t)(c_cur + lane) * a.row_stride + fp, b, e);  // 0 <= fp < range (:655)
-  }
+  // directory probe of (cell, fp): cell and fp are clamped into the table; fp >= range (empty or
+  // out-of-range fingerprint, :655) is turned into an empty list where the word is unpacked
+  auto probe = [&](DirWord<IT>& d, uint32_t cell, uint32_t fp) {
+    d.load(a.dir, (size_t)min(cell, a.F - 1) * a.row_stride + min(fp, a.range - 1));
+  };
+  DirWord<IT> dw, dw_next;
+  uint32_t fp_cur = 0xFFFFFFFFu;
+  if (c_cur + lane < a.F) fp_cur = (uint32_t)__ldg(&sk[c_cur + lane]);
+  probe(dw, c_cur + lane, fp_cur);
+  // R = rounds of 32 postings whose gathers issue together (one batch); D = batches in flight
+  static_assert(D == 2 || D == 3, "ring depth");
+  uint32_t lbuf[D][R];  // ring of gathered batches
+  uint32_t live[D];     // rounds each one holds (warp-uniform)
+#pragma unroll
+  for (int d = 0; d < D; ++d) live[d] = 0;
+  uint32_t phase = 0;
+  auto drain = [&](uint32_t (&l)[R], uint32_t nl) {
+    if (nl >= (uint32_t)R) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) count(l[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < R - 1; ++k)
+        if ((uint32_t)k < nl) count(l[k]);
+    }
+  };
   for (; c_cur < a.F; c_cur += step) {
     const uint32_t cell = c_cur + lane;
+    if (warp == 0 && c_cur % kPfCells == 0) prefetch_chunk(a, pf, c_cur / kPfCells + kPfAhead);
     // prefetch: fingerprint of group +2, directory word of group +1
     fp_next2 = 0xFFFFFFFFu;
     if (c_cur + 2 * step + lane < a.F) fp_next2 = (uint32_t)__ldg(&sk[c_cur + 2 * step + lane]);
-    uint32_t nb = 0, ne = 0;
-    if (fp_next < a.range) load_dir<IT>(a.dir, (size_t)(cell + step) * a.row_stride + fp_next, nb, ne);
+    probe(dw_next, cell + step, fp_next);
 
-    const uint32_t len = e - b;
+    const uint32_t b = dw.begin(), len = fp_cur < a.range ? dw.end() - b : 0u;
     uint32_t incl = len;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -117,30 +222,58 @@ __global__ void __launch_bounds__(NT) query_count_kernel(QueryArgs a, uint64_t q
     if (len) s_src[warp][__popc(nonempty & (le >> 1))] = (IDX)((IDX)cell * a.gid_stride + b - excl);
     __syncwarp();
     gathered += len;
-    uint32_t starts_before = 0;
-    constexpr int R = 4;  // rounds of 32 postings whose loads are in flight together
-    for (uint32_t r0 = 0; r0 < total; r0 += 32 * R) {
-      uint32_t l[R];
+    // The 32 lists are walked as one concatenated stream, 32 slots per round.  rel = distance from
+    // the round's first slot to this lane's list start: a list starts inside the round iff
+    // rel < 32 (it wraps to a huge value once the start is behind; empty lists never start).
+    uint32_t rel = len ? excl : 0x80000000u;
+    const IDX* rank_ptr = &s_src[warp][0] - 1;  // &s_src[warp][lists started before the round - 1]
+    uint32_t s = lane;
+    // Batches of R rounds: the R owner look-ups and gathers of a batch are independent and issue
+    // back to back; the batch gathered before it (possibly by the previous group) is counted while
+    // they are in flight.  D register buffers rotate under a warp-uniform branch so that no
+    // register copy ever has to wait for a gather.
+    // gather NB <= R rounds into l[0..NB) (straight-line code per NB, so the partial last batch of a
+    // group costs exactly its rounds)
+    auto gather_n = [&](uint32_t (&l)[R], auto nb_tag) {
+      constexpr int NB = decltype(nb_tag)::value;
 #pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const uint32_t rel = excl - (r0 + 32 * k);  // wraps to a huge value when the list starts before this round
-        const unsigned m = __reduce_or_sync(kFull, (len && rel < 32u) ? 1u << rel : 0u);
-        const uint32_t s = r0 + 32 * k + lane;
-        l[k] = 0xFFFFFFFFu;
-        if (s < total) {
-          const uint32_t owner = starts_before + __popc(m & le) - 1;
-          l[k] = gids[s_src[warp][owner] + s];
-        }
-        starts_before += __popc(m);
+      for (int k = 0; k < NB; ++k) {
+        const unsigned m = __reduce_or_sync(kFull, shl_clamp(1u, rel));  // list starts inside this round
+        const IDX at = rank_ptr[__popc(m & le)] + s + 32 * k;  // owner = last list started at or before s
+        l[k] = gids[s + 32 * k < total ? at : dead_at];       // past the end: this lane's dummy id
+        rank_ptr += __popc(m);
+        rel -= 32;
       }
-#pragma unroll
-      for (int k = 0; k < R; ++k)
-        if (l[k] != 0xFFFFFFFFu) count(l[k]);
+      s += 32 * NB;
+    };
+    auto gather = [&](uint32_t (&l)[R], uint32_t nb) {  // nb warp-uniform, 1..R
+      if (nb >= (uint32_t)R) gather_n(l, std::integral_constant<int, R>());
+      else if (R > 3 && nb == 3) gather_n(l, std::integral_constant<int, (R > 3 ? 3 : 1)>());
+      else if (R > 2 && nb == 2) gather_n(l, std::integral_constant<int, (R > 2 ? 2 : 1)>());
+      else gather_n(l, std::integral_constant<int, 1>());
+    };
+    for (uint32_t r0 = 0; r0 < total; r0 += 32 * R) {
+      const uint32_t nb = min((uint32_t)R, (total - r0 + 31) >> 5);
+      // fill buffer `phase`, count the oldest one ((phase+1) % D, filled D-1 batches ago)
+      if (D == 2) {
+        if (phase == 0) { gather(lbuf[0], nb); drain(lbuf[1], live[1]); live[0] = nb; }
+        else { gather(lbuf[1], nb); drain(lbuf[0], live[0]); live[1] = nb; }
+      } else {
+        if (phase == 0) { gather(lbuf[0], nb); drain(lbuf[1], live[1]); live[0] = nb; }
+        else if (phase == 1) { gather(lbuf[1], nb); drain(lbuf[2], live[2]); live[1] = nb; }
+        else { gather(lbuf[2], nb); drain(lbuf[0], live[0]); live[2] = nb; }
+      }
+      phase = phase + 1 == D ? 0 : phase + 1;
     }
     __syncwarp();
-    b = nb; e = ne;
+    dw = dw_next;
+    fp_cur = fp_next;
     fp_next = fp_next2;
   }
+  // the D-1 batches still in flight: every buffer but `phase`, which was drained by the last step
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+    if ((uint32_t)d != phase) drain(lbuf[d], live[d]);
   __syncthreads();
 
   auto count_of = [&](uint32_t g) -> uint32_t {
@@ -207,30 +340,57 @@ using namespace nq;
 
 template <typename IT, int MODE, int NT>
 static cudaError_t launch_query_t(size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st) {
-  const bool idx32 = (uint64_t)a.F * a.gid_stride < (1ull << 32);
-  cudaError_t e;
-  if (idx32) {
-    e = cudaFuncSetAttribute(query_count_kernel<IT, MODE, NT, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    query_count_kernel<IT, MODE, NT, uint32_t><<<nb, NT, smem, st>>>(a, q0);
-  } else {
-    e = cudaFuncSetAttribute(query_count_kernel<IT, MODE, NT, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    query_count_kernel<IT, MODE, NT, uint64_t><<<nb, NT, smem, st>>>(a, q0);
-  }
+  const bool idx32 = (uint64_t)a.F * a.gid_stride + kQuerySlack < (1ull << 32);
+  auto k32 = query_count_kernel<IT, MODE, NT, uint32_t>;
+  auto k64 = query_count_kernel<IT, MODE, NT, uint64_t>;
+  cudaError_t e = cudaFuncSetAttribute(idx32 ? k32 : k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (idx32) k32<<<nb, NT, smem, st>>>(a, q0);
+  else k64<<<nb, NT, smem, st>>>(a, q0);
   return cudaSuccess;
 }
 template <typename IT>
 static cudaError_t launch_query_it(int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st) {
-  // small counter arrays: 256-thread CTAs so that 8 queries share an SM; large ones: one big CTA
-  const bool small = smem <= 24 * 1024;
-  if (mode == kPack16) return small ? launch_query_t<IT, kPack16, 256>(smem, nb, a, q0, st) : launch_query_t<IT, kPack16, 1024>(smem, nb, a, q0, st);
-  if (mode == kSmem32) return small ? launch_query_t<IT, kSmem32, 256>(smem, nb, a, q0, st) : launch_query_t<IT, kSmem32, 1024>(smem, nb, a, q0, st);
+  // small counter arrays: 128-thread CTAs (4 warps with ~56 registers each carry a deep gather
+  // pipeline, and ~9 queries share an SM); large ones: one big CTA per SM
+  const bool small = smem <= 26 * 1024;  // at least 8 such CTAs per SM
+  if (mode == kPack16) return small ? launch_query_t<IT, kPack16, 128>(smem, nb, a, q0, st) : launch_query_t<IT, kPack16, 1024>(smem, nb, a, q0, st);
+  if (mode == kSmem32) return small ? launch_query_t<IT, kSmem32, 128>(smem, nb, a, q0, st) : launch_query_t<IT, kSmem32, 1024>(smem, nb, a, q0, st);
   return launch_query_t<IT, kGlobal32, 512>(0, nb, a, q0, st);
 }
 static cudaError_t launch_query(uint32_t elem, int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0,
                                 cudaStream_t st) {
   return elem == 2 ? launch_query_it<uint16_t>(mode, smem, nb, a, q0, st) : launch_query_it<uint32_t>(mode, smem, nb, a, q0, st);
+}
+
+// counter mode and dynamic shared memory of the query kernel for this index
+static void query_layout(const nq_index* ix, int& mode, size_t& smem) {
+  // counters + 32 spare words (dummy targets of the branch-free count) + the kernel's static shared memory
+  const size_t spare = 128, fixed = 4096, optin = ix->ctx->smem_optin;
+  const size_t pack = (size_t)((ix->n + 1) / 2) * 4, full = (size_t)ix->n * 4;
+  if (ix->p.S <= 15 && pack + spare + fixed <= optin) { mode = kPack16; smem = pack + spare; }
+  else if (full + spare + fixed <= optin) { mode = kSmem32; smem = full + spare; }
+  else { mode = kGlobal32; smem = 0; }
+}
+
+// Writes the 32 dummy ids behind the posting arrays (kQuerySlack elements are reserved there).
+int nq_query_prepare(nq_index* ix) {
+  int mode;
+  size_t smem;
+  query_layout(ix, mode, smem);
+  const uint32_t words = mode == kPack16 ? (ix->n + 1) / 2 : ix->n;
+  uint16_t h16[32];
+  uint32_t h32[32];
+  for (uint32_t l = 0; l < 32; ++l) {
+    h32[l] = query_dummy_id<uint32_t>(mode, words, l);
+    h16[l] = (uint16_t)query_dummy_id<uint16_t>(mode, words, l);
+    if (ix->elem == 2 && mode != kGlobal32 && h32[l] > 0xFFFFu) return nq_set_error(NQ_ERR_INVALID, "dummy id overflow");
+  }
+  char* end = static_cast<char*>(ix->d_gids) + (size_t)ix->p.F * ix->gid_stride * ix->elem;
+  NQ_CUDA(cudaMemcpyAsync(end, ix->elem == 2 ? (const void*)h16 : (const void*)h32, 32 * ix->elem, cudaMemcpyHostToDevice,
+                          ix->ctx->stream));
+  NQ_CUDA(cudaStreamSynchronize(ix->ctx->stream));  // the staging arrays live on this stack frame
+  return NQ_OK;
 }
 
 int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t min_score, nq_hits** out) {
@@ -253,9 +413,7 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
 
   int mode;
   size_t smem;
-  if (p.S <= 15 && (size_t)((ix->n + 1) / 2) * 4 <= ctx->smem_optin) { mode = kPack16; smem = (size_t)((ix->n + 1) / 2) * 4; }
-  else if ((size_t)ix->n * 4 <= ctx->smem_optin) { mode = kSmem32; smem = (size_t)ix->n * 4; }
-  else { mode = kGlobal32; smem = 0; }
+  query_layout(ix, mode, smem);
 
   // queries per launch: everything at once unless global counters would be too large
   uint64_t q_per_launch = nq;
