@@ -17,6 +17,7 @@
 // column is streamed with several 64-byte loads in flight per warp; 16+ warps per SM keep the
 // serial cursor chain of the ordered sweep covered.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "device_common.cuh"
@@ -163,6 +164,214 @@ __global__ void __launch_bounds__(256) cell_sort_kernel(const uint16_t* __restri
   if (lane == 0 && posted) atomicAdd(total_postings, posted);  // `posted` is only maintained by lane 0
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Compact form (n <= kMaxCompact, u16 ids): one CTA per cell, everything in shared memory.
+//   1. histogram of the cell's column (packed u16 counters, shared atomics)
+//   2. block scan -> per-list begin; the directory row {begin,end} goes out coalesced
+//   3. scatter with a RETURNING shared atomic on the list cursor, genomes taken in blocks of 2*NT
+//      with a barrier in between: every genome gets a slot of its list, out of gid order only
+//      against genomes of its own block
+//   4. restore gid order inside every list: lists are tiny (2.4 genomes on average at n = 10k), so a
+//      thread insertion-sorts the (almost sorted) lists of its bins; a list longer than kSerialSort is rebuilt by
+//      the whole CTA from a bitmap of its members (ids are distinct, so enumerating the set bits IS
+//      the sorted list) - near-duplicate genomes make such lists, random ones do not
+//   5. the cell's posting array goes out with 16-byte stores
+// The column is read twice (the second pass hits L2) instead of being staged, which keeps the
+// footprint at 2 B per genome + 8 KB and 8 CTAs on an SM at n = 10k.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kSerialSort = 32;
+
+template <int NT>
+__global__ void __launch_bounds__(NT) cell_build_kernel(const uint16_t* __restrict__ fpT, uint32_t n, uint32_t n_pad,
+                                                        uint32_t range, uint32_t* __restrict__ dir,
+                                                        uint32_t row_stride, uint16_t* __restrict__ gids,
+                                                        uint32_t gid_stride, uint32_t max_long,
+                                                        unsigned long long* __restrict__ total_postings) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ uint32_t s_warp[NT / 32];
+  __shared__ uint32_t s_nlong;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t cell = blockIdx.x;
+  constexpr unsigned kFull = 0xFFFFFFFFu;
+  // shared layout: cursors (packed u16) | out ids (u16) | bitmap | long-list bins (u16)
+  const uint32_t cur_words = (max(range / 2, 1u) + 3) & ~3u;  // keeps `out` 16-byte aligned
+  uint32_t* cur = smem;
+  uint16_t* out = reinterpret_cast<uint16_t*>(cur + cur_words);
+  uint32_t* bitmap = reinterpret_cast<uint32_t*>(out + n_pad);  // n_pad is a multiple of 32: stays 4-byte aligned
+  uint16_t* long_bins = reinterpret_cast<uint16_t*>(bitmap + n_pad / 32);
+  const uint16_t* col = fpT + (size_t)cell * n_pad;
+  const uint4* col4 = reinterpret_cast<const uint4*>(col);  // n_pad * 2 B is a multiple of 64 B
+  const uint32_t nvec = n_pad / 8;
+
+  for (uint32_t i = tid; i < cur_words; i += NT) cur[i] = 0;
+  if (tid == 0) s_nlong = 0;
+  __syncthreads();
+
+  // ---- 1. histogram
+  auto for_each_fp = [&](auto&& f) {
+    for (uint32_t v = tid; v < nvec; v += NT) {
+      const uint4 q = __ldg(col4 + v);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t lo = w[j] & 0xFFFFu, hi = w[j] >> 16;
+        if (lo != kNoPost) f(lo, v * 8 + 2 * j);
+        if (hi != kNoPost) f(hi, v * 8 + 2 * j + 1);
+      }
+    }
+  };
+  for_each_fp([&](uint32_t fp, uint32_t) { atomicAdd(&cur[fp >> 1], 1u << ((fp & 1) * 16)); });
+  __syncthreads();
+
+  // ---- 2. exclusive scan over the bins; thread t owns bins [t*bpt, (t+1)*bpt), bpt even
+  const uint32_t bpt = max(2u, range / NT);
+  const uint32_t bin0 = tid * bpt;
+  const bool owner = bin0 < range;
+  uint32_t mine = 0;
+  if (owner)
+    for (uint32_t k = 0; k < bpt / 2; ++k) {
+      const uint32_t w = cur[bin0 / 2 + k];
+      mine += (w & 0xFFFFu) + (w >> 16);
+    }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFull, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t base = incl - mine;
+  for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
+  uint32_t posted = 0;
+  for (uint32_t w = 0; w < NT / 32; ++w) posted += s_warp[w];
+  if (owner) {
+    uint32_t* myrow = dir + (size_t)cell * row_stride + bin0;
+    uint32_t run = base;
+    for (uint32_t k = 0; k < bpt / 2; ++k) {
+      const uint32_t w = cur[bin0 / 2 + k];
+      const uint32_t c0 = w & 0xFFFFu, c1 = w >> 16;
+      const uint32_t b0 = run, b1 = run + c0;
+      run = b1 + c1;
+      cur[bin0 / 2 + k] = b0 | (b1 << 16);  // cursors start at the list begins
+      if (range >= 2) {
+        myrow[2 * k] = b0 | (b1 << 16);       // {begin, end} of bin 2k
+        myrow[2 * k + 1] = b1 | (run << 16);  // and of bin 2k+1
+      } else {
+        myrow[0] = b0 | (b1 << 16);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. scatter (second pass over the column): slot = cursor++ of the genome's list.  The CTA
+  // walks the genomes in blocks of 2*NT with a barrier per block, so a list can only be out of gid
+  // order between genomes of the same block: step 4 then sees almost sorted lists (~L compares).
+  {
+    const uint32_t* col32 = reinterpret_cast<const uint32_t*>(col);
+    const uint32_t npairs = n_pad / 2, rounds = (npairs + NT - 1) / NT;
+    uint32_t w_next = tid < npairs ? __ldg(col32 + tid) : 0xFFFFFFFFu;
+    for (uint32_t r = 0; r < rounds; ++r) {
+      const uint32_t w = w_next, p = r * NT + tid;
+      w_next = p + NT < npairs ? __ldg(col32 + p + NT) : 0xFFFFFFFFu;
+      const uint32_t fps[2] = {w & 0xFFFFu, w >> 16};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (fps[j] != kNoPost) {
+          const uint32_t sh = (fps[j] & 1) * 16;
+          const uint32_t old = atomicAdd(&cur[fps[j] >> 1], 1u << sh);
+          out[(old >> sh) & 0xFFFFu] = (uint16_t)(2 * p + j);
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- 4. gid order inside every list.  After the scatter cursor[bin] == end of bin == begin of bin+1.
+  // Cursor words (two bins each) are dealt round-robin: fingerprints are heavily skewed (a few
+  // hundred neighbouring bins hold most postings) and neighbouring lanes then get lists of similar
+  // length.  Lists arrive almost sorted, so the common case per element is one load and one compare.
+  for (uint32_t wi = tid; wi < range / 2; wi += NT) {
+    const uint32_t w = cur[wi];
+    uint32_t b = wi ? cur[wi - 1] >> 16 : 0u;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t e = h ? w >> 16 : w & 0xFFFFu;
+      const uint32_t len = e - b;
+      if (len > kSerialSort) {
+        const uint32_t at = atomicAdd(&s_nlong, 1u);
+        if (at < max_long) long_bins[at] = (uint16_t)(2 * wi + h);
+      } else if (len > 1) {
+        uint32_t prev = out[b];
+        for (uint32_t i = b + 1; i < e; ++i) {
+          const uint32_t x = out[i];
+          if (x >= prev) {
+            prev = x;
+            continue;
+          }
+          uint32_t j = i;  // insert x into the sorted prefix; its maximum (prev) ends up at i
+          do {
+            out[j] = out[j - 1];
+            --j;
+          } while (j > b && out[j - 1] > x);
+          out[j] = (uint16_t)x;
+        }
+      }
+      b = e;
+    }
+  }
+  __syncthreads();
+  const uint32_t nlong = min(s_nlong, max_long);  // max_long >= n / (kSerialSort+1) + 1: never exceeded
+  const uint32_t nwords = n_pad / 32;
+  const uint32_t wpt = (nwords + NT - 1) / NT;  // bitmap words per thread, contiguous
+  for (uint32_t li = 0; li < nlong; ++li) {
+    const uint32_t bin = long_bins[li];
+    const uint32_t e = (cur[bin >> 1] >> ((bin & 1) * 16)) & 0xFFFFu;
+    const uint32_t b = bin ? (cur[(bin - 1) >> 1] >> (((bin - 1) & 1) * 16)) & 0xFFFFu : 0u;
+    for (uint32_t i = tid; i < nwords; i += NT) bitmap[i] = 0;
+    __syncthreads();
+    for (uint32_t i = b + tid; i < e; i += NT) {
+      const uint32_t g = out[i];
+      atomicOr(&bitmap[g >> 5], 1u << (g & 31));
+    }
+    __syncthreads();
+    uint32_t cnt = 0;
+    for (uint32_t k = 0; k < wpt; ++k) {
+      const uint32_t w = tid * wpt + k;
+      if (w < nwords) cnt += __popc(bitmap[w]);
+    }
+    uint32_t inc2 = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, inc2, d);
+      if (lane >= d) inc2 += t;
+    }
+    __syncthreads();  // s_warp reuse
+    if (lane == 31) s_warp[warp] = inc2;
+    __syncthreads();
+    uint32_t pos = b + inc2 - cnt;
+    for (uint32_t w = 0; w < warp; ++w) pos += s_warp[w];
+    for (uint32_t k = 0; k < wpt; ++k) {
+      const uint32_t w = tid * wpt + k;
+      if (w >= nwords) break;
+      uint32_t bits = bitmap[w];
+      while (bits) {
+        const uint32_t bit = __ffs(bits) - 1;
+        bits &= bits - 1;
+        out[pos++] = (uint16_t)(w * 32 + bit);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- 5. posting array of the cell (gid_stride * 2 B is a multiple of 32 B)
+  uint4* dst = reinterpret_cast<uint4*>(gids + (size_t)cell * gid_stride);
+  const uint4* src = reinterpret_cast<const uint4*>(out);
+  for (uint32_t v = tid; v < (posted + 7) / 8; v += NT) dst[v] = src[v];
+  if (tid == 0 && posted) atomicAdd(total_postings, (unsigned long long)posted);
+}
+
 }  // namespace nq
 
 using namespace nq;
@@ -184,6 +393,28 @@ static cudaError_t launch_cell_sort(nq_ctx* ctx, const uint16_t* d_fpT, uint32_t
                                                             static_cast<typename DirEntry<IT>::type*>(ix->d_row),
                                                             ix->row_stride, static_cast<IT*>(ix->d_gids), ix->gid_stride,
                                                             d_total);
+  ctx->launches++;
+  return cudaPeekAtLastError();
+}
+
+// compact form: one CTA per cell.  Returns cudaErrorInvalidValue when the cell does not fit in shared memory.
+static cudaError_t launch_cell_build(nq_ctx* ctx, const uint16_t* d_fpT, uint32_t n, uint32_t n_pad, nq_index* ix,
+                                     unsigned long long* d_total) {
+  const uint32_t range = (uint32_t)ix->p.range, F = ix->p.F;
+  const uint32_t max_long = n / (kSerialSort + 1) + 1;
+  const size_t smem = (size_t)((std::max(range / 2, 1u) + 3) & ~3u) * 4 + (size_t)n_pad * 2 + n_pad / 8 + (((size_t)max_long * 2 + 15) & ~(size_t)15);
+  if (smem + 2048 > ctx->smem_optin || range < 2) return cudaErrorInvalidValue;
+  const bool big = smem > 56 * 1024;
+  cudaError_t e = big ? cudaFuncSetAttribute(cell_build_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : cudaFuncSetAttribute(cell_build_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  NqTimer timer(ctx, NQK_CELLSORT);
+  if (big)
+    cell_build_kernel<1024><<<F, 1024, smem, ctx->stream>>>(d_fpT, n, n_pad, range, static_cast<uint32_t*>(ix->d_row), ix->row_stride,
+                                                           static_cast<uint16_t*>(ix->d_gids), ix->gid_stride, max_long, d_total);
+  else
+    cell_build_kernel<256><<<F, 256, smem, ctx->stream>>>(d_fpT, n, n_pad, range, static_cast<uint32_t*>(ix->d_row), ix->row_stride,
+                                                         static_cast<uint16_t*>(ix->d_gids), ix->gid_stride, max_long, d_total);
   ctx->launches++;
   return cudaPeekAtLastError();
 }
@@ -232,8 +463,11 @@ int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketch
     transpose_fp_kernel<<<tg, 256, 0, ctx->stream>>>(d_sketches, d_fpT, n, F, n_pad, range);
   }
   ctx->launches++;
-  e = ix->elem == 2 ? launch_cell_sort<uint16_t>(ctx, d_fpT, n, n_pad, ix, d_total)
-                    : launch_cell_sort<uint32_t>(ctx, d_fpT, n, n_pad, ix, d_total);
+  e = cudaErrorInvalidValue;
+  if (ix->elem == 2 && !getenv("NQ_CELL_SORT_WARP")) e = launch_cell_build(ctx, d_fpT, n, n_pad, ix, d_total);
+  if (e == cudaErrorInvalidValue)  // u32 ids, or a cell that does not fit in shared memory: one warp per cell
+    e = ix->elem == 2 ? launch_cell_sort<uint16_t>(ctx, d_fpT, n, n_pad, ix, d_total)
+                      : launch_cell_sort<uint32_t>(ctx, d_fpT, n, n_pad, ix, d_total);
   if (e != cudaSuccess) return fail(nq_set_error(NQ_ERR_CUDA, "cell_sort launch failed: %s", cudaGetErrorString(e)));
   unsigned long long total = 0;
   if ((e = cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||

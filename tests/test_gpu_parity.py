@@ -292,6 +292,32 @@ def test_sharded_query_equals_single(nb, ctx):
         assert np.array_equal(merged, (c[seg].astype(np.uint64) << np.uint64(32)) | gid[seg])
 
 
+@pytest.mark.parametrize("n", [5_000, 30_000, 65_400, 70_000])
+def test_index_build_synthetic_sketches(nb, ctx, n):
+    """Index build on raw sketches: skewed fingerprints, lists far longer than a warp (clusters of
+    identical genomes), unposted cells (-1 and fp >= 2^W), u16 -> u32 id switch at 65400."""
+    rng = np.random.default_rng(n)
+    ps = dict(K=31, S=5, W=12, H=4)
+    F = 32
+    o = oracle(J=0.2, **ps)
+    g = gpu_index(nb, ctx, J=0.2, **ps)
+    sks = (rng.integers(0, 4096, size=(n, F)) & rng.integers(0, 4096, size=(n, F))).astype(np.int32)  # skewed to small values
+    clones = rng.random(n) < 0.3
+    sks[clones] = sks[0]                          # 30% identical genomes: one list of ~0.3 n per cell
+    sks[rng.random((n, F)) < 0.01] = -1
+    sks[rng.random((n, F)) < 0.01] = 5000         # out of range: not posted
+    g.insert_sketches(sks)
+    o.insert_sketches(sks)
+    rp, ogids = o.csr()
+    sizes, gids = g.export_postings()
+    assert np.array_equal(sizes, np.diff(rp).astype(np.uint32))
+    assert np.array_equal(gids, ogids)
+    q = np.concatenate([sks[:3], sks[n // 2:n // 2 + 3]])
+    ptr, c, gid = g.query_sketches(q)
+    ohp, oc, og = o.query_batch(q)
+    assert np.array_equal(ptr, ohp) and np.array_equal(c, oc) and np.array_equal(gid, og)
+
+
 def test_large_n_global_counter_path(nb, ctx):
     """More genomes than fit in shared-memory counters: counters move to HBM."""
     rng = np.random.default_rng(41)
