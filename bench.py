@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-genomes", type=int, default=0, help="genomes per GPU in the e2e leg (default: all that fit host RAM)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "q100k"],
+                    help="c2: the contract line (default).  q100k: secondary line, query sketches/s against a 100k-genome "
+                         "index split over the GPUs (BASELINE metric, second half); genomes are sketched in batches")
     return ap.parse_args()
 
 
@@ -210,10 +213,148 @@ def cpu_baseline(args, cores):
 
 
 # ------------------------------------------------------------------------------------------------
+def run_q100k(args):
+    """Secondary line: query sketches/s against a 100k-genome index (configs[2]: 10k queries, minjac 0.1),
+    the index split by gid over the GPUs (strong scaling: total work fixed).  Sequences never persist:
+    genomes are generated and sketched in batches, only the sketches and the index stay in HBM."""
+    import torch
+    import torch.distributed as dist
+
+    import niqki_b200
+    from niqki_b200.capi import check, lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    Gt = args.genomes or 100_000
+    Qt = args.queries or 10_000
+    G, Q, L = Gt // world, Qt // world, args.genome_len
+    Lc = lib()
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = niqki_b200.Context(local, stream)
+    ix = niqki_b200.Index(S=S, K=K, W=W, H=H, min_fract=J, ctx=ctx)
+    F = ix.F
+    g0, q0 = rank * G, rank * Q
+    B = 4000
+    buf = torch.empty(B * L + 64, dtype=torch.uint8, device=dev)
+    sk_idx = torch.empty((G, F), dtype=torch.int32, device=dev)
+    sk_qry = torch.empty((Q, F), dtype=torch.int32, device=dev)
+    t_build = time.perf_counter()
+    for b0 in range(0, G, B):
+        nb = min(B, G - b0)
+        check(Lc.nq_synth_genomes_device(ctx.h, SEED, g0 + b0, nb, L, C.c_void_p(buf.data_ptr())))
+        ix.compute_sketches(buf, np.arange(nb + 1, dtype=np.uint64) * L, out=sk_idx[b0:b0 + nb])
+    ix.insert_sketches(sk_idx, gid_base=g0)
+    del sk_idx
+    for b0 in range(0, Q, B):
+        nb = min(B, Q - b0)
+        qid = np.arange(q0 + b0, q0 + b0 + nb, dtype=np.uint64)
+        parents = (qid % np.uint64(Gt)).astype(np.uint64)
+        thr = thresholds([RATES[int(q) % 3] for q in qid])
+        check(Lc.nq_synth_mutants_device(ctx.h, SEED, parents.ctypes.data, qid.ctypes.data, thr.ctypes.data, nb, L,
+                                         C.c_void_p(buf.data_ptr())))
+        ix.compute_sketches(buf, np.arange(nb + 1, dtype=np.uint64) * L, out=sk_qry[b0:b0 + nb])
+    del buf
+    sk_all = torch.empty((Q * world, F), dtype=torch.int32, device=dev) if world > 1 else sk_qry
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        if world > 1:
+            dist.all_gather_into_tensor(sk_all, sk_qry)
+        ix.query_sketches(sk_all, fetch=False)
+
+    for _ in range(args.warmup):
+        step()
+    ctx.set_timing(True)
+    ctx.timing_reset()
+    launches0 = ctx.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    q_ms, q_n = ctx.timing()["query"]
+    gathered = ctx.last_query_gathered
+    launches = ctx.launches - launches0
+    ctx.set_timing(False)
+    # e2e: host query sketches in, sorted hit lists out, through the C ABI
+    h_sk = torch.empty((Q * world, F), dtype=torch.int32, pin_memory=True)
+    h_sk.copy_(sk_all)
+    torch.cuda.synchronize()
+    n_sk = h_sk.numpy()
+    ptr, cnt, gid = ix.query_sketches(n_sk)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ptr, cnt, gid = ix.query_sketches(n_sk)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    first_hits = [int(gid[int(ptr[i])]) if ptr[i + 1] > ptr[i] else -1 for i in range(8)]
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        nq_total = Q * world
+        q_bytes = 4 * gathered + nq_total * F * (8 + 2)
+        q_gbs = q_bytes / (q_ms / max(q_n, 1) / 1e3) / 1e9 if q_ms else None
+        info = ix.info()
+        line = {"metric": "query sketches/s vs 100k-genome index (10k mutated-copy queries, minjac 0.1)",
+                "value": nq_total * args.steps / (ms_total / 1e3), "unit": "query sketches/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": f"secondary (not the contract line): {Gt} synthetic {L} bp genomes indexed, gid-sharded over "
+                                       f"{world} GPU(s), {nq_total} mutated-copy queries all-gathered and counted on every shard",
+                           "K": K, "S": S, "W": W, "H": H, "minjac": J, "genomes_per_gpu": G, "queries_total": nq_total,
+                           "l2": "per-step index traffic far larger than L2 (>= 1 GB of postings gathered per GPU)"},
+                "index_postings_per_gpu": info["n_postings"], "index_build_wall_s": t_build,
+                "roofline": {"kernel": "query_count_kernel", "bound": "hbm", "achieved": q_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": (q_gbs / hbm_peak) if q_gbs else None, "traffic": None,
+                             "algorithmic_bytes": q_bytes, "gathered_postings": gathered, "launches": int(q_n),
+                             "ms_per_launch": q_ms / max(q_n, 1),
+                             "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback"},
+                "e2e": {"value": nq_total * args.steps / float(dt.item()), "unit": "query sketches/s",
+                        "h2d_bytes_per_step": int(n_sk.nbytes), "d2h_bytes_per_step": int(ptr.nbytes + cnt.nbytes + gid.nbytes),
+                        "note": "nq_query_batch with pinned host sketches; sorted hit lists copied out"},
+                "gpu_launches": int(launches), "clocks": clocks, "first_hits": first_hits}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "q100k":
+        return run_q100k(args)
 
     import torch
     import torch.distributed as dist
@@ -383,9 +524,17 @@ def main():
         except (OSError, ValueError):
             pass
 
-        def ncu_traffic(kernel):
+        def ncu_traffic(kernel, scale=1.0):
             t = traffic.get(kernel)
-            return t["dram_bytes_per_launch"] if t and t.get("genomes_per_gpu") == G and t.get("queries") == nq_total else None
+            ok = t and t.get("genomes_per_gpu") == G and t.get("queries") == nq_total
+            return int(t["dram_bytes_per_launch"] * scale) if ok else None
+
+        b_ms, b_n = kt["cell_sort"]
+        t_ms, t_n = kt["transpose"]
+        # index build, minimal bytes per posting: u16 fingerprint in, u16 gid out, + the directory
+        elem = 2 if G <= 65400 else 4
+        b_bytes = info["n_postings"] * 2 * elem + F * (1 << W) * 2 * elem
+        b_gbs = b_bytes / (b_ms / max(b_n, 1) / 1e3) / 1e9 if b_ms else None
 
         line = {
             "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
@@ -402,7 +551,8 @@ def main():
             "roofline": {"kernel": "sketch_scan_kernel", "bound": "int32-alu",
                          "achieved": scan_gbases * OPS_PER_BASE / 1e3 if scan_gbases else None, "peak": int_peak,
                          "unit": "Tint32-op/s", "frac": (scan_gbases * OPS_PER_BASE / 1e3 / int_peak) if scan_gbases else None,
-                         "traffic": ncu_traffic("sketch_scan_kernel"),
+                         # ncu captured the index launch (G entries); scaled to the average launch of this run
+                         "traffic": ncu_traffic("sketch_scan_kernel", bases_per_scan / (G * L)),
                          "algorithmic_ops_per_base": OPS_PER_BASE, "gbases_per_s": scan_gbases,
                          "launches": int(scan_n), "ms_per_launch": scan_ms / max(scan_n, 1),
                          "peak_source": "148 SMs x 128 int32 lanes x SM clock sampled during the run (no measured INT32 "
@@ -416,6 +566,10 @@ def main():
                                "traffic": ncu_traffic("query_count_kernel"), "peak_source": peak_src,
                                "algorithmic_bytes": q_bytes, "gathered_postings": gathered,
                                "launches": int(q_n), "ms_per_launch": q_ms / max(q_n, 1)},
+            "roofline_build": {"kernel": "cell_build_kernel", "bound": "hbm", "achieved": b_gbs, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": (b_gbs / hbm_peak) if b_gbs else None, "traffic": ncu_traffic("cell_build_kernel"),
+                               "algorithmic_bytes": b_bytes, "launches": int(b_n), "ms_per_launch": b_ms / max(b_n, 1),
+                               "note": "instruction-issue bound (59% issue-active, shared-memory atomics): profiles/r01_ncu_cb5.txt"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "first_hits": first_hits,
         }
         if not args.no_cpu_baseline and world == 1:

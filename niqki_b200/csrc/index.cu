@@ -17,7 +17,6 @@
 // column is streamed with several 64-byte loads in flight per warp; 16+ warps per SM keep the
 // serial cursor chain of the ordered sweep covered.
 #include <algorithm>
-#include <cstdlib>
 #include <vector>
 
 #include "device_common.cuh"
@@ -31,7 +30,7 @@ constexpr uint16_t kNoPost = 0xFFFFu;
 __global__ void __launch_bounds__(256) transpose_fp_kernel(const int32_t* __restrict__ sk, uint16_t* __restrict__ fpT,
                                                            uint32_t n, uint32_t F, uint32_t n_pad, uint32_t range) {
   __shared__ uint16_t tile[32][34];
-  const uint32_t c0 = blockIdx.x * 32, g0 = blockIdx.y * 32;
+  const uint32_t c0 = blockIdx.y * 32, g0 = blockIdx.x * 32;  // genomes along x: no 65535-block limit
   const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -456,15 +455,15 @@ int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketch
   if ((st = nq_dmalloc(ctx, (void**)&d_total, 8)) != NQ_OK) return fail(st);
   if (cudaMemsetAsync(d_total, 0, 8, ctx->stream) != cudaSuccess) return fail(nq_set_error(NQ_ERR_CUDA, "memset failed"));
 
-  dim3 tg((F + 31) / 32, (n_pad + 31) / 32);
-  if (tg.y > 65535) return fail(nq_set_error(NQ_ERR_UNSUPPORTED, "more than 2M genomes per build call"));
+  dim3 tg((n_pad + 31) / 32, (F + 31) / 32);
+  if (tg.y > 65535) return fail(nq_set_error(NQ_ERR_UNSUPPORTED, "S > 21 is not supported by the index build"));
   {
     NqTimer timer(ctx, NQK_TRANSPOSE);
     transpose_fp_kernel<<<tg, 256, 0, ctx->stream>>>(d_sketches, d_fpT, n, F, n_pad, range);
   }
   ctx->launches++;
   e = cudaErrorInvalidValue;
-  if (ix->elem == 2 && !getenv("NQ_CELL_SORT_WARP")) e = launch_cell_build(ctx, d_fpT, n, n_pad, ix, d_total);
+  if (ix->elem == 2) e = launch_cell_build(ctx, d_fpT, n, n_pad, ix, d_total);
   if (e == cudaErrorInvalidValue)  // u32 ids, or a cell that does not fit in shared memory: one warp per cell
     e = ix->elem == 2 ? launch_cell_sort<uint16_t>(ctx, d_fpT, n, n_pad, ix, d_total)
                       : launch_cell_sort<uint32_t>(ctx, d_fpT, n, n_pad, ix, d_total);

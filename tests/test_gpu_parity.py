@@ -318,13 +318,14 @@ def test_index_build_synthetic_sketches(nb, ctx, n):
     assert np.array_equal(ptr, ohp) and np.array_equal(c, oc) and np.array_equal(gid, og)
 
 
-def test_large_n_global_counter_path(nb, ctx):
-    """More genomes than fit in shared-memory counters: counters move to HBM."""
+@pytest.mark.parametrize("n", [150_000, 2_200_000])
+def test_large_n_global_counter_path(nb, ctx, n):
+    """More genomes than fit in shared-memory counters: counters move to HBM (2.2M: the entry
+    count of a reads-as-entries index, beyond the old 2M-per-build limit)."""
     rng = np.random.default_rng(41)
     ps = dict(K=31, S=4, W=6, H=3)
     o = oracle(J=0.5, **ps)
     g = gpu_index(nb, ctx, J=0.5, **ps)
-    n = 150_000
     sks = rng.integers(0, 64, size=(n, 16)).astype(np.int32)
     sks[rng.random((n, 16)) < 0.01] = -1
     g.insert_sketches(sks)
