@@ -40,6 +40,7 @@ struct QueryArgs {
   uint64_t* hit_begin;  // [nq]
   uint32_t* hit_n;      // [nq]
   uint32_t* gcounts;    // global counters [gridDim.x][n] (GLOBAL mode only)
+  uint32_t prefetch;    // cooperative L2 prefetch of upcoming cells (only when a few chunks of cells fit in L2)
 };
 
 enum CountMode { kPack16 = 0, kSmem32 = 1, kGlobal32 = 2 };
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 9 : 1) query_count_kernel(Quer
   constexpr unsigned kFull = 0xFFFFFFFFu;
 
   PfSlice pf{};
-  if (warp == 0) {
+  if (warp == 0 && a.prefetch) {
     pf = make_pf_slice(a, sizeof(IT), lane);
     for (uint32_t ch = 0; ch < kPfAhead; ++ch) prefetch_chunk(a, pf, ch);
   }
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 9 : 1) query_count_kernel(Quer
   };
   for (; c_cur < a.F; c_cur += step) {
     const uint32_t cell = c_cur + lane;
-    if (warp == 0 && c_cur % kPfCells == 0) prefetch_chunk(a, pf, c_cur / kPfCells + kPfAhead);
+    if (warp == 0 && a.prefetch && c_cur % kPfCells == 0) prefetch_chunk(a, pf, c_cur / kPfCells + kPfAhead);
     // prefetch: fingerprint of group +2, directory word of group +1
     fp_next2 = 0xFFFFFFFFu;
     if (c_cur + 2 * step + lane < a.F) fp_next2 = (uint32_t)__ldg(&sk[c_cur + 2 * step + lane]);
@@ -248,9 +249,21 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 9 : 1) query_count_kernel(Quer
     };
     auto gather = [&](uint32_t (&l)[R], uint32_t nb) {  // nb warp-uniform, 1..R
       if (nb >= (uint32_t)R) gather_n(l, std::integral_constant<int, R>());
-      else if (R > 3 && nb == 3) gather_n(l, std::integral_constant<int, (R > 3 ? 3 : 1)>());
-      else if (R > 2 && nb == 2) gather_n(l, std::integral_constant<int, (R > 2 ? 2 : 1)>());
-      else gather_n(l, std::integral_constant<int, 1>());
+      else if (R == 4 && nb == 3) gather_n(l, std::integral_constant<int, (R == 4 ? 3 : 1)>());
+      else if (R == 4 && nb == 2) gather_n(l, std::integral_constant<int, (R == 4 ? 2 : 1)>());
+      else if (R == 4) gather_n(l, std::integral_constant<int, 1>());
+      else {  // deep batches (long lists): the one partial batch of a group goes round by round
+#pragma unroll
+        for (int k = 0; k < R - 1; ++k)
+          if ((uint32_t)k < nb) {
+            const unsigned m = __reduce_or_sync(kFull, shl_clamp(1u, rel));
+            const IDX at = rank_ptr[__popc(m & le)] + s;
+            l[k] = gids[s < total ? at : dead_at];
+            rank_ptr += __popc(m);
+            rel -= 32;
+            s += 32;
+          }
+      }
     };
     for (uint32_t r0 = 0; r0 < total; r0 += 32 * R) {
       const uint32_t nb = min((uint32_t)R, (total - r0 + 31) >> 5);
@@ -341,8 +354,10 @@ using namespace nq;
 template <typename IT, int MODE, int NT>
 static cudaError_t launch_query_t(size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st) {
   const bool idx32 = (uint64_t)a.F * a.gid_stride + kQuerySlack < (1ull << 32);
-  auto k32 = query_count_kernel<IT, MODE, NT, uint32_t>;
-  auto k64 = query_count_kernel<IT, MODE, NT, uint64_t>;
+  // one big CTA per SM (many genomes, long lists, HBM-bound): 8 gathers per batch for bytes in flight
+  constexpr int R = NT == 1024 ? 8 : 4;
+  auto k32 = query_count_kernel<IT, MODE, NT, uint32_t, R>;
+  auto k64 = query_count_kernel<IT, MODE, NT, uint64_t, R>;
   cudaError_t e = cudaFuncSetAttribute(idx32 ? k32 : k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (idx32) k32<<<nb, NT, smem, st>>>(a, q0);
@@ -414,6 +429,8 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
   int mode;
   size_t smem;
   query_layout(ix, mode, smem);
+  // the prefetch window (kPfAhead + 1 chunks of kPfCells cells: directory rows + posting arrays) must sit in L2
+  a.prefetch = (uint64_t)(kPfAhead + 1) * kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem <= (64ull << 20);
 
   // queries per launch: everything at once unless global counters would be too large
   uint64_t q_per_launch = nq;
