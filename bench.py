@@ -48,9 +48,12 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-genomes", type=int, default=0, help="genomes per GPU in the e2e leg (default: all that fit host RAM)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "q100k"],
+    ap.add_argument("--reads", type=int, default=0, help="c4: reads per GPU (default 10M)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "q100k", "c4", "c5"],
                     help="c2: the contract line (default).  q100k: secondary line, query sketches/s against a 100k-genome "
-                         "index split over the GPUs (BASELINE metric, second half); genomes are sketched in batches")
+                         "index split over the GPUs (BASELINE metric, second half); genomes are sketched in batches.  "
+                         "c4: configs[3], --indexlines/--querylines on 10M synthetic 150 bp reads (S=8).  "
+                         "c5: configs[4], all-vs-all --matrix of 20k genomes at S=18, rows tiled over the GPUs")
     return ap.parse_args()
 
 
@@ -349,12 +352,251 @@ def run_q100k(args):
         dist.destroy_process_group()
 
 
+def _setup(args):
+    import torch
+    import torch.distributed as dist
+
+    import niqki_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = niqki_b200.Context(local, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    return torch, dist, niqki_b200, world, rank, local, dev, stream, ctx, barrier, timed
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        return {}
+
+
+def run_c4(args):
+    """Secondary line, configs[3]: --indexlines on N synthetic 150 bp reads (S=8, W=12, K=31: SURVEY 8d),
+    then --querylines on a subset.  Step = sketch + densify every read, build the index, count the
+    query subset.  Reads are sharded by id over the GPUs like genomes."""
+    from niqki_b200.capi import check, lib
+
+    torch, dist, niqki_b200, world, rank, local, dev, stream, ctx, barrier, timed = _setup(args)
+    S4, RL = 8, 150
+    N = args.reads or 10_000_000
+    Q = args.queries or 2_000
+    Lc = lib()
+    ix = niqki_b200.Index(S=S4, K=K, W=W, H=H, min_fract=J, ctx=ctx)
+    F = ix.F
+    r0 = rank * N
+    d_reads = torch.empty(N * RL + 64, dtype=torch.uint8, device=dev)
+    check(Lc.nq_synth_reads_device(ctx.h, SEED, r0, N, GENOME_LEN, RL, C.c_void_p(d_reads.data_ptr())))
+    offs = np.arange(N + 1, dtype=np.uint64) * RL
+    sk = torch.empty((N, F), dtype=torch.int32, device=dev)
+    fl = torch.empty(N, dtype=torch.int32, device=dev)
+    sk_all = torch.empty((Q * world, F), dtype=torch.int32, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+
+    def step_index():
+        ix.compute_sketches(d_reads, offs, out=sk, flags=fl)
+        ix.insert_sketches(sk, gid_base=r0)
+
+    def step_query():
+        q = sk[:Q]
+        if world > 1:
+            dist.all_gather_into_tensor(sk_all, q.contiguous())
+            q = sk_all
+        ix.query_sketches(q, fetch=False)
+
+    for _ in range(args.warmup):
+        step_index()
+    step_query()
+    ctx.set_timing(True)
+    ctx.timing_reset()
+    launches0 = ctx.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_index = timed(step_index, args.steps)
+    ms_query = timed(step_query, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    kt = ctx.timing()
+    launches = ctx.launches - launches0
+    gathered = ctx.last_query_gathered
+    ctx.set_timing(False)
+    ptr, cnt, gid = ix.query_sketches(sk[:8])
+    first_hits = [int(gid[int(ptr[i])]) if ptr[i + 1] > ptr[i] else -1 for i in range(8)]
+    # e2e: host reads in (pinned), sketches out, index built from them, sorted hits of the query subset out
+    Ne = min(N, 2_000_000)
+    h_reads = torch.empty(Ne * RL, dtype=torch.uint8, pin_memory=True)
+    h_reads.copy_(d_reads[: Ne * RL])
+    h_sk = torch.empty((Ne, F), dtype=torch.int32, pin_memory=True)
+    torch.cuda.synchronize()
+    n_reads, n_sk = h_reads.numpy(), h_sk.numpy()
+    eo = np.arange(Ne + 1, dtype=np.uint64) * RL
+    d2h = [0]
+
+    def step_e2e():
+        ix.compute_sketches(n_reads, eo, out=n_sk)
+        ix.insert_sketches(n_sk, gid_base=r0)
+        p_, c_, g_ = ix.query_sketches(n_sk[:Q])
+        d2h[0] = n_sk.nbytes + p_.nbytes + c_.nbytes + g_.nbytes
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    step_e2e()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peaks = _peaks()
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        q_ms, q_n = kt["query"]
+        nq_total = Q * world
+        q_bytes = 4 * gathered + nq_total * F * (8 + 2)
+        q_gbs = q_bytes / (q_ms / max(q_n, 1) / 1e3) / 1e9 if q_ms else None
+        line = {"metric": "Gbases/s sketched + indexed (--indexlines on 150 bp reads)", "value": N * RL * world * args.steps / (ms_index / 1e3) / 1e9,
+                "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_index / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": f"secondary (not the contract line) configs[3]: {N} synthetic {RL} bp reads per GPU --indexlines, "
+                                       f"then --querylines on {nq_total} of them, x{world} GPUs", "K": K, "S": S4, "W": W, "H": H, "minjac": J,
+                           "l2": "inputs larger than L2 (1.5 GB of reads, 10 GB of sketches per step)"},
+                "reads_per_s": N * world * args.steps / (ms_index / 1e3),
+                "query_sketches_per_s": nq_total * args.steps / (ms_query / 1e3), "query_ms_per_step": ms_query / args.steps,
+                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt.items()},
+                "roofline": {"kernel": "query_count_kernel", "bound": "hbm", "achieved": q_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": (q_gbs / hbm_peak) if q_gbs else None, "traffic": None, "algorithmic_bytes": q_bytes,
+                             "gathered_postings": gathered, "launches": int(q_n), "ms_per_launch": q_ms / max(q_n, 1)},
+                "e2e": {"value": Ne * RL * world / float(dt.item()) / 1e9, "unit": "Gbases/s", "reads": Ne,
+                        "h2d_bytes_per_step": int(n_reads.nbytes + n_sk.nbytes + Q * F * 4), "d2h_bytes_per_step": int(d2h[0])},
+                "gpu_launches": int(launches), "clocks": clocks, "first_hits": first_hits}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_c5(args):
+    """Secondary line, configs[4]: all-vs-all --matrix of N genomes at S=18.  Every rank sketches its
+    slice of the genomes, the sketches are all-gathered, every rank builds the whole index and
+    computes its block of rows.  Timed: the matrix rows (device counting + D2H of the
+    dense counts); sketching and index build are reported beside it."""
+    from niqki_b200.capi import check, lib
+
+    torch, dist, niqki_b200, world, rank, local, dev, stream, ctx, barrier, timed = _setup(args)
+    S5 = 18
+    N = args.genomes or 20_000
+    L = args.genome_len
+    Lc = lib()
+    ix = niqki_b200.Index(S=S5, K=K, W=W, H=H, min_fract=J, ctx=ctx)
+    F = ix.F
+    per = (N + world - 1) // world
+    g0, g1 = rank * per, min(N, (rank + 1) * per)
+    B = 2000
+    buf = torch.empty(B * L + 64, dtype=torch.uint8, device=dev)
+    sk = torch.empty((per * world, F), dtype=torch.int32, device=dev)
+    mine = sk[g0:g0 + per]
+    ctx.set_timing(True)
+    ctx.timing_reset()
+    torch.cuda.synchronize()
+    t_sk = time.perf_counter()
+    for b0 in range(g0, g1, B):
+        nb = min(B, g1 - b0)
+        check(Lc.nq_synth_genomes_device(ctx.h, SEED, b0, nb, L, C.c_void_p(buf.data_ptr())))
+        ix.compute_sketches(buf, np.arange(nb + 1, dtype=np.uint64) * L, out=sk[b0:b0 + nb])
+    torch.cuda.synchronize()
+    t_sk = time.perf_counter() - t_sk
+    scan_ms, scan_n = ctx.timing()["scan"]
+    del buf
+    if world > 1:
+        dist.all_gather_into_tensor(sk, mine.clone())
+    t_ix = time.perf_counter()
+    ix.insert_sketches(sk[:N], gid_base=0)
+    torch.cuda.synchronize()
+    t_ix = time.perf_counter() - t_ix
+    del sk, mine
+    rows = g1 - g0
+    out = {}
+
+    def step():
+        out["m"] = ix.query_range(g0, g1, wrap16=True)
+
+    step()
+    ctx.timing_reset()
+    launches0 = ctx.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    m_ms, m_n = ctx.timing()["matrix"]
+    launches = ctx.launches - launches0
+    m = out["m"]
+    diag_ok = bool(np.all(m[np.arange(rows), np.arange(g0, g1)] == (F & 0xFFFF)))
+    if rank == 0:
+        sec = float(dt.item()) / args.steps
+        pair_incr = float(m.astype(np.float64).sum()) * world  # ~ total increments (this rank's rows x ranks)
+        line = {"metric": "genome pairs/s (all-vs-all --matrix, S=18)", "value": N * N / sec, "unit": "pairs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": f"secondary (not the contract line) configs[4]: --matrix of {N} synthetic {L} bp genomes, S={S5}, "
+                                       f"rows tiled over {world} GPU(s)", "K": K, "S": S5, "W": W, "H": H,
+                           "l2": "index (directory + postings) far larger than L2"},
+                "matrix_device_ms_per_step": m_ms / args.steps, "matrix_kernel_launches": int(m_n),
+                "pair_increments_per_s": pair_incr / (m_ms / args.steps / 1e3) if m_ms else None,
+                "sketch_gbases_per_s": (g1 - g0) * L / (scan_ms / 1e3) / 1e9 if scan_ms else None, "sketch_wall_s": t_sk,
+                "index_build_wall_s": t_ix, "diag_is_F_mod_65536": diag_ok,
+                "e2e": {"value": N * N / sec, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(m.nbytes),
+                        "note": "nq_matrix_rows: dense u32 counts of this rank's rows copied to the host"},
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "q100k":
         return run_q100k(args)
+    if args.workload == "c4":
+        return run_c4(args)
+    if args.workload == "c5":
+        return run_c5(args)
 
     import torch
     import torch.distributed as dist
@@ -456,10 +698,11 @@ def main():
     # for the index call and of the sorted hit lists), on as many genomes as the host can pin
     e2e = None
     if not args.no_e2e:
-        avail = mem_available_bytes()
+        # every rank of the node pins its own copy: split what the host has left between them
+        avail = mem_available_bytes() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
         Ge = args.e2e_genomes or G
         need = (Ge + Q) * L + (Ge + Q) * F * 4
-        while Ge > 64 and avail and need * 1.3 > avail:
+        while Ge > 64 and avail and need * 1.5 > avail:
             Ge //= 2
             need = (Ge + Q) * L + (Ge + Q) * F * 4
         Qe = max(1, min(Q, Ge // 10))

@@ -117,4 +117,5 @@ constexpr uint32_t kMaxCompact = 65400;  // genomes per shard in the u16 form (l
 constexpr uint32_t kQuerySlack = 64;     // elements reserved behind d_gids[F][gid_stride]
 int nq_query_prepare(nq_index* ix);      // fills that slack; call once the index arrays exist
 int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t min_score, nq_hits** out);
+int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t wrap_mask, uint32_t* d_out);
 int nq_matrix_impl(nq_index* ix, uint32_t row_begin, uint32_t row_end, int wrap16, uint32_t* h_counts);

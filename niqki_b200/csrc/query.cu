@@ -21,6 +21,7 @@
 // the host when it merges shards.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include <vector>
 
@@ -41,6 +42,7 @@ struct QueryArgs {
   uint32_t* hit_n;      // [nq]
   uint32_t* gcounts;    // global counters [gridDim.x][n] (GLOBAL mode only)
   uint32_t prefetch;    // cooperative L2 prefetch of upcoming cells (only when a few chunks of cells fit in L2)
+  uint32_t* dense;      // when set: row q of [nq][n] takes every genome's count instead of the thresholded hit list (--matrix)
 };
 
 enum CountMode { kPack16 = 0, kSmem32 = 1, kGlobal32 = 2 };
@@ -131,14 +133,83 @@ __device__ __forceinline__ void prefetch_chunk(const QueryArgs& a, const PfSlice
   if (p.len[1]) l2_prefetch_bulk(static_cast<const char*>(a.gids) + (size_t)chunk * p.pitch[1] + p.off[1], p.len[1]);
 }
 
+// ---- threshold (:661-665) + compaction, shared by both gather forms: count the hits, reserve a pool
+// segment with one atomicAdd, then write (count, gid) in gid order
+template <int MODE, int NT>
+__device__ __forceinline__ void query_finish(const QueryArgs& a, uint64_t q, const uint32_t* cnt, uint32_t gathered) {
+  __shared__ uint32_t s_warp[NT / 32];
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_total;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr unsigned kFull = 0xFFFFFFFFu;
+  auto count_of = [&](uint32_t g) -> uint32_t {
+    uint32_t c;
+    if (MODE == kPack16) c = (cnt[g >> 1] >> ((g & 1) * 16)) & 0xFFFFu;
+    else if (MODE == kGlobal32) c = __ldcg(&cnt[g]);
+    else c = cnt[g];
+    return c & a.wrap_mask;
+  };
+
+  if (a.dense) {  // all-vs-all rows (:570-598): the whole counter array, coalesced
+    uint32_t* row = a.dense + q * a.n;
+    for (uint32_t g = tid; g < a.n; g += NT) row[g] = count_of(g);
+    return;
+  }
+  uint32_t mine = 0;
+  for (uint32_t g = tid; g < a.n; g += NT) mine += count_of(g) >= a.min_score;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    mine += __shfl_xor_sync(kFull, mine, d);
+    gathered += __shfl_xor_sync(kFull, gathered, d);
+  }
+  if (lane == 0) {
+    s_warp[warp] = mine;
+    if (gathered) atomicAdd(a.cursor + 1, (unsigned long long)gathered);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < NT / 32; ++w) t += s_warp[w];
+    s_total = t;
+    s_base = atomicAdd(a.cursor, (unsigned long long)t);
+    a.hit_begin[q] = s_base;
+    a.hit_n[q] = t;
+  }
+  __syncthreads();
+  const uint32_t total = s_total;
+  const unsigned long long base = s_base;
+  if (total == 0 || base + total > a.pool_cap) return;  // overflow: host re-runs with a larger pool
+
+  uint32_t done = 0;
+  for (uint32_t g0 = 0; g0 < a.n; g0 += NT) {
+    const uint32_t g = g0 + tid;
+    uint32_t c = 0;
+    bool hit = false;
+    if (g < a.n) {
+      c = count_of(g);
+      hit = c >= a.min_score;
+    }
+    if (__syncthreads_count(hit) == 0) continue;  // hits are sparse: most chunks of NT genomes hold none
+    const unsigned bal = __ballot_sync(kFull, hit);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, chunk = 0;
+    for (int w = 0; w < NT / 32; ++w) {
+      const uint32_t x = s_warp[w];
+      before += w < (int)warp ? x : 0;
+      chunk += x;
+    }
+    if (hit) a.pool[base + done + before + __popc(bal & ((1u << lane) - 1))] = ((uint64_t)c << 32) | (a.gid_base + g);
+    done += chunk;
+    __syncthreads();  // s_warp is rewritten by the next chunk that holds a hit
+  }
+}
+
 // IDX = uint32_t when every posting index F*gid_stride fits 32 bits (always for S <= 15 in the compact form)
 template <typename IT, int MODE, int NT, typename IDX, int R = 4, int D = 2>
 __global__ void __launch_bounds__(NT, NT == 128 ? 9 : 1) query_count_kernel(QueryArgs a, uint64_t q0) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ IDX s_src[NT / 32][32];  // per warp: stream base of the rank-th non-empty list
-  __shared__ uint32_t s_warp[NT / 32];
-  __shared__ unsigned long long s_base;
-  __shared__ uint32_t s_total;
   const uint64_t q = q0 + blockIdx.x;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t* cnt = MODE == kGlobal32 ? a.gcounts + (size_t)blockIdx.x * a.n : smem;
@@ -289,62 +360,151 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 9 : 1) query_count_kernel(Quer
     if ((uint32_t)d != phase) drain(lbuf[d], live[d]);
   __syncthreads();
 
-  auto count_of = [&](uint32_t g) -> uint32_t {
-    uint32_t c;
-    if (MODE == kPack16) c = (cnt[g >> 1] >> ((g & 1) * 16)) & 0xFFFFu;
-    else if (MODE == kGlobal32) c = __ldcg(&cnt[g]);
-    else c = cnt[g];
-    return c & a.wrap_mask;
+  query_finish<MODE, NT>(a, q, cnt, gathered);
+}
+
+// ---- segment-table form --------------------------------------------------------------------------
+// The concatenated-stream walk above finds the owner of every stream slot in every round (REDUX +
+// 2 POPC + LDS per 32 postings).  Here the lists of a warp's 32 cells are cut into SEGMENTS of SEG
+// consecutive postings (SEG = 32: a whole round per segment, for shards whose lists are tens of
+// postings long; SEG = 8: four lists side by side per round, for short lists) and the descriptors
+// {first posting, postings left in the list} of the group's segments are written, in list order,
+// into a small per-warp table in shared memory: each cell's lane writes the segments of its own
+// list at the position a warp scan of the segment counts gives it.  The gather of a round is then
+// one broadcast LDS.64 of the descriptor + add, compare, select, address, load — no look-up — and
+// rounds are independent of each other, so the R gathers of a batch issue back to back.  Lists
+// longer than the table are taken in windows of T segments.  Same register ring of two R-round
+// batches as the stream form (the previous batch is counted while this one's loads fly), same
+// dummy-id trick for the dead lanes of a list's last segment.
+template <typename IDX>
+struct SegRef {
+  IDX at;       // index of the segment's first posting in gids[]
+  int32_t rem;  // postings of the list from there on (lanes at or past it are dead)
+};
+
+template <typename IT, int MODE, int NT, typename IDX, int SEG, int T, int R>
+__global__ void __launch_bounds__(NT, NT == 128 ? 8 : 1) query_count_seg_kernel(QueryArgs a, uint64_t q0) {
+  constexpr int SPR = 32 / SEG;  // segments per round
+  static_assert(SEG == 8 || SEG == 16 || SEG == 32, "segment size");
+  static_assert(T % SPR == 0, "table = whole rounds");
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ __align__(16) SegRef<IDX> s_tab[NT / 32][T + SPR];
+  const uint64_t q = q0 + blockIdx.x;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* cnt = MODE == kGlobal32 ? a.gcounts + (size_t)blockIdx.x * a.n : smem;
+  const uint32_t words = MODE == kPack16 ? (a.n + 1) / 2 : a.n;
+  constexpr unsigned kFull = 0xFFFFFFFFu;
+
+  PfSlice pf{};
+  if (warp == 0 && a.prefetch) {
+    pf = make_pf_slice(a, sizeof(IT), lane);
+    for (uint32_t ch = 0; ch < kPfAhead; ++ch) prefetch_chunk(a, pf, ch);
+  }
+  for (uint32_t i = tid; i < words; i += NT) cnt[i] = 0;
+  __syncthreads();
+
+  const int32_t* sk = a.qsk + q * a.F;
+  const IT* gids = static_cast<const IT*>(a.gids);
+  SegRef<IDX>* tab = s_tab[warp];
+  const uint32_t sub = lane & (SEG - 1), grp = lane / SEG;
+  uint32_t gathered = 0;
+  const uint32_t dummy = query_dummy_id<IT>(MODE, words, lane);
+  const IDX dead_at = (IDX)a.F * a.gid_stride + lane;
+  auto count = [&](uint32_t l) {
+    if (MODE == kPack16) atomicAdd(&smem[l >> 1], (l & 1) * 0xFFFFu + 1u);
+    else if (MODE == kSmem32) atomicAdd(&smem[l], 1u);
+    else if (l != dummy) atomicAdd(&cnt[l], 1u);
   };
+  const uint32_t step = NT;
+  uint32_t c_cur = warp * 32;
+  uint32_t fp_next = 0xFFFFFFFFu, fp_next2 = 0xFFFFFFFFu;
+  if (c_cur + step + lane < a.F) fp_next = (uint32_t)__ldg(&sk[c_cur + step + lane]);
+  auto probe = [&](DirWord<IT>& d, uint32_t cell, uint32_t fp) {
+    d.load(a.dir, (size_t)min(cell, a.F - 1) * a.row_stride + min(fp, a.range - 1));
+  };
+  DirWord<IT> dw, dw_next;
+  uint32_t fp_cur = 0xFFFFFFFFu;
+  if (c_cur + lane < a.F) fp_cur = (uint32_t)__ldg(&sk[c_cur + lane]);
+  probe(dw, c_cur + lane, fp_cur);
 
-  // ---- threshold (:661-665): count hits, reserve a pool segment, then write them in gid order
-  uint32_t mine = 0;
-  for (uint32_t g = tid; g < a.n; g += NT) mine += count_of(g) >= a.min_score;
+  uint32_t lbuf[2][R];
+  uint32_t live0 = 0, live1 = 0;
+  uint32_t phase = 0;
+  auto drain = [&](uint32_t (&l)[R], uint32_t nl) {
+    if (nl >= (uint32_t)R) {
 #pragma unroll
-  for (int d = 16; d; d >>= 1) {
-    mine += __shfl_xor_sync(kFull, mine, d);
-    gathered += __shfl_xor_sync(kFull, gathered, d);
-  }
-  if (lane == 0) {
-    s_warp[warp] = mine;
-    if (gathered) atomicAdd(a.cursor + 1, (unsigned long long)gathered);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t t = 0;
-    for (int w = 0; w < NT / 32; ++w) t += s_warp[w];
-    s_total = t;
-    s_base = atomicAdd(a.cursor, (unsigned long long)t);
-    a.hit_begin[q] = s_base;
-    a.hit_n[q] = t;
-  }
-  __syncthreads();
-  const uint32_t total = s_total;
-  const unsigned long long base = s_base;
-  if (total == 0 || base + total > a.pool_cap) return;  // overflow: host re-runs with a larger pool
+      for (int k = 0; k < R; ++k) count(l[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < R - 1; ++k)
+        if ((uint32_t)k < nl) count(l[k]);
+    }
+  };
+  // gather nb (1..R, warp-uniform) rounds starting at table position t0 (a multiple of SPR)
+  auto gather = [&](uint32_t (&l)[R], const SegRef<IDX>* t0, uint32_t nb) {
+    if (nb >= (uint32_t)R) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const SegRef<IDX> d = t0[k * SPR + grp];
+        l[k] = gids[(int32_t)sub < d.rem ? d.at + sub : dead_at];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < R - 1; ++k)
+        if ((uint32_t)k < nb) {
+          const SegRef<IDX> d = t0[k * SPR + grp];
+          l[k] = gids[(int32_t)sub < d.rem ? d.at + sub : dead_at];
+        }
+    }
+  };
+  for (; c_cur < a.F; c_cur += step) {
+    const uint32_t cell = c_cur + lane;
+    if (warp == 0 && a.prefetch && c_cur % kPfCells == 0) prefetch_chunk(a, pf, c_cur / kPfCells + kPfAhead);
+    fp_next2 = 0xFFFFFFFFu;
+    if (c_cur + 2 * step + lane < a.F) fp_next2 = (uint32_t)__ldg(&sk[c_cur + 2 * step + lane]);
+    probe(dw_next, cell + step, fp_next);
 
-  uint32_t done = 0;
-  for (uint32_t g0 = 0; g0 < a.n; g0 += NT) {
-    const uint32_t g = g0 + tid;
-    uint32_t c = 0;
-    bool hit = false;
-    if (g < a.n) {
-      c = count_of(g);
-      hit = c >= a.min_score;
+    const uint32_t b = dw.begin(), len = fp_cur < a.range ? dw.end() - b : 0u;
+    const uint32_t nseg = (len + SEG - 1) / SEG;
+    uint32_t incl = nseg;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d) incl += t;
     }
-    const unsigned bal = __ballot_sync(kFull, hit);
-    __syncthreads();  // s_warp reuse
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t before = 0, chunk = 0;
-    for (int w = 0; w < NT / 32; ++w) {
-      const uint32_t x = s_warp[w];
-      before += w < (int)warp ? x : 0;
-      chunk += x;
+    const uint32_t excl = incl - nseg;
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    const IDX first = (IDX)cell * a.gid_stride + b;
+    gathered += len;
+
+    for (uint32_t w0 = 0; w0 < total; w0 += T) {  // windows of T segments
+      const uint32_t nwin = min((uint32_t)T, total - w0);
+      // this lane's segments that fall into the window
+      const uint32_t lo = max(excl, w0), hi = min(incl, w0 + T);
+      for (uint32_t sg = lo; sg < hi; ++sg) {
+        const uint32_t k = (sg - excl) * SEG;
+        tab[sg - w0] = SegRef<IDX>{(IDX)(first + k), (int32_t)(len - k)};
+      }
+      if (SPR > 1 && lane < SPR) tab[nwin + lane] = SegRef<IDX>{0, 0};  // dead slots of the last round
+      __syncwarp();
+      const uint32_t rounds = (nwin + SPR - 1) / SPR;
+      for (uint32_t r0 = 0; r0 < rounds; r0 += R) {
+        const uint32_t nb = min((uint32_t)R, rounds - r0);
+        // fill buffer `phase`, count the other one (gathered one batch ago, maybe by the previous group)
+        if (phase == 0) { gather(lbuf[0], tab + r0 * SPR, nb); drain(lbuf[1], live1); live0 = nb; }
+        else { gather(lbuf[1], tab + r0 * SPR, nb); drain(lbuf[0], live0); live1 = nb; }
+        phase ^= 1;
+      }
+      __syncwarp();  // the table is rewritten by the next window / group
     }
-    if (hit) a.pool[base + done + before + __popc(bal & ((1u << lane) - 1))] = ((uint64_t)c << 32) | (a.gid_base + g);
-    done += chunk;
+    dw = dw_next;
+    fp_cur = fp_next;
+    fp_next = fp_next2;
   }
+  if (phase == 0) drain(lbuf[1], live1);
+  else drain(lbuf[0], live0);
+  __syncthreads();
+  query_finish<MODE, NT>(a, q, cnt, gathered);
 }
 
 }  // namespace nq
@@ -352,7 +512,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 9 : 1) query_count_kernel(Quer
 using namespace nq;
 
 template <typename IT, int MODE, int NT>
-static cudaError_t launch_query_t(size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st) {
+static cudaError_t launch_query_t(size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st, int* occ) {
   const bool idx32 = (uint64_t)a.F * a.gid_stride + kQuerySlack < (1ull << 32);
   // one big CTA per SM (many genomes, long lists, HBM-bound): 8 gathers per batch for bytes in flight
   constexpr int R = NT == 1024 ? 8 : 4;
@@ -360,28 +520,98 @@ static cudaError_t launch_query_t(size_t smem, unsigned nb, const QueryArgs& a, 
   auto k64 = query_count_kernel<IT, MODE, NT, uint64_t, R>;
   cudaError_t e = cudaFuncSetAttribute(idx32 ? k32 : k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  if (occ)  // resident CTAs per SM of the kernel that would run (wave sizing), no launch
+    return idx32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k32, NT, smem)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k64, NT, smem);
   if (idx32) k32<<<nb, NT, smem, st>>>(a, q0);
   else k64<<<nb, NT, smem, st>>>(a, q0);
   return cudaSuccess;
 }
+template <typename IT, int MODE, int NT, int SEG, int T>
+static cudaError_t launch_query_seg_t(size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st, int* occ) {
+  const bool idx32 = (uint64_t)a.F * a.gid_stride + kQuerySlack < (1ull << 32);
+  constexpr int R = NT == 128 ? 4 : 8;
+  // 64-bit posting indexes only occur with global counters (n > 131k at S=15), where shared memory is free
+  auto k32 = query_count_seg_kernel<IT, MODE, NT, uint32_t, SEG, T, R>;
+  auto k64 = query_count_seg_kernel<IT, MODE, NT, uint64_t, SEG, T / 2, R>;  // 16-byte descriptors: half the window
+  // the segment table is static shared memory on top of the counters: cudaErrorInvalidValue here
+  // (counters + table over the per-block limit) sends the caller back to the stream form
+  cudaError_t e = cudaFuncSetAttribute(idx32 ? k32 : k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (occ)  // resident CTAs per SM of the kernel that would run (wave sizing), no launch
+    return idx32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k32, NT, smem)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k64, NT, smem);
+  if (idx32) k32<<<nb, NT, smem, st>>>(a, q0);
+  else k64<<<nb, NT, smem, st>>>(a, q0);
+  return cudaSuccess;
+}
+// Gather form.  Lists of a shard of n genomes hold ~n * 6.8e-4 postings on bacterial sketches at the
+// default W.  NQ_QUERY_FORM = stream | seg8 | seg16 | seg32 overrides (measurement only).
+enum QueryForm { kFormStream = 0, kFormSeg8 = 8, kFormSeg16 = 16, kFormSeg32 = 32 };
+static int query_form(const QueryArgs& a, bool small) {
+  static const char* env = getenv("NQ_QUERY_FORM");
+  if (env) {
+    if (!strcmp(env, "stream")) return kFormStream;
+    if (!strcmp(env, "seg8")) return kFormSeg8;
+    if (!strcmp(env, "seg16")) return kFormSeg16;
+    if (!strcmp(env, "seg32")) return kFormSeg32;
+  }
+  if (small) return kFormStream;
+  return a.n >= 40000 ? kFormSeg32 : kFormStream;
+}
 template <typename IT>
-static cudaError_t launch_query_it(int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st) {
+static cudaError_t launch_query_it(int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st, int* occ) {
   // small counter arrays: 128-thread CTAs (4 warps with ~56 registers each carry a deep gather
   // pipeline, and ~9 queries share an SM); large ones: one big CTA per SM
   const bool small = smem <= 26 * 1024;  // at least 8 such CTAs per SM
-  if (mode == kPack16) return small ? launch_query_t<IT, kPack16, 128>(smem, nb, a, q0, st) : launch_query_t<IT, kPack16, 1024>(smem, nb, a, q0, st);
-  if (mode == kSmem32) return small ? launch_query_t<IT, kSmem32, 128>(smem, nb, a, q0, st) : launch_query_t<IT, kSmem32, 1024>(smem, nb, a, q0, st);
-  return launch_query_t<IT, kGlobal32, 512>(0, nb, a, q0, st);
+  const int form = query_form(a, small);
+  if (mode == kGlobal32) {
+    if (form == kFormStream) return launch_query_t<IT, kGlobal32, 512>(0, nb, a, q0, st, occ);
+    return launch_query_seg_t<IT, kGlobal32, 512, 32, 96>(0, nb, a, q0, st, occ);
+  }
+#define NQ_SEG_DISPATCH(MODE)                                                                                      \
+  if (small) {                                                                                                     \
+    if (form == kFormSeg8) return launch_query_seg_t<IT, MODE, 128, 8, 64>(smem, nb, a, q0, st, occ);                   \
+    if (form == kFormSeg16) return launch_query_seg_t<IT, MODE, 128, 16, 64>(smem, nb, a, q0, st, occ);                 \
+    if (form == kFormSeg32) return launch_query_seg_t<IT, MODE, 128, 32, 64>(smem, nb, a, q0, st, occ);                 \
+    return launch_query_t<IT, MODE, 128>(smem, nb, a, q0, st, occ);                                                     \
+  }                                                                                                                \
+  if (form == kFormSeg8) return launch_query_seg_t<IT, MODE, 1024, 8, 96>(smem, nb, a, q0, st, occ);                    \
+  if (form == kFormSeg16) return launch_query_seg_t<IT, MODE, 1024, 16, 96>(smem, nb, a, q0, st, occ);                  \
+  if (form == kFormSeg32) return launch_query_seg_t<IT, MODE, 1024, 32, 96>(smem, nb, a, q0, st, occ);                  \
+  return launch_query_t<IT, MODE, 1024>(smem, nb, a, q0, st, occ);
+  if (mode == kPack16) { NQ_SEG_DISPATCH(kPack16) }
+  NQ_SEG_DISPATCH(kSmem32)
+#undef NQ_SEG_DISPATCH
 }
 static cudaError_t launch_query(uint32_t elem, int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0,
-                                cudaStream_t st) {
-  return elem == 2 ? launch_query_it<uint16_t>(mode, smem, nb, a, q0, st) : launch_query_it<uint32_t>(mode, smem, nb, a, q0, st);
+                                cudaStream_t st, int* occ = nullptr) {
+  return elem == 2 ? launch_query_it<uint16_t>(mode, smem, nb, a, q0, st, occ) : launch_query_it<uint32_t>(mode, smem, nb, a, q0, st, occ);
+}
+
+// Queries per launch.  Global counters bound it by memory.  When the L2 prefetch is on (a few
+// chunks of cells fit in L2: the co-resident CTAs share what each of them pulls in, as long as
+// they sweep the cells in step), more queries than CTA slots are cut into equal launches of at most
+// one resident wave: CTAs of one launch start together and stay in step, whereas a single grid
+// refills slots one by one and ends up with every CTA at a different cell, i.e. random DRAM
+// access for two dependent sectors per probe (measured at 12.5k genomes x 10k queries: 13.2 ms
+// as one grid).
+static uint64_t query_wave(const nq_index* ix, int mode, size_t smem, const QueryArgs& a, uint64_t nq) {
+  if (mode == kGlobal32) return std::max<uint64_t>(1, std::min<uint64_t>(nq, (1ull << 30) / ((uint64_t)ix->n * 4)));
+  static const char* env = getenv("NQ_QUERY_WAVES");  // "0": one grid (measurement only)
+  if (!a.prefetch || (env && env[0] == '0')) return nq;
+  int occ = 0;
+  if (launch_query(ix->elem, mode, smem, 1, a, 0, nullptr, &occ) != cudaSuccess || occ <= 0) return nq;
+  const uint64_t slots = (uint64_t)occ * ix->ctx->sm_count;
+  if (nq <= slots) return nq;
+  const uint64_t waves = (nq + slots - 1) / slots;
+  return (nq + waves - 1) / waves;
 }
 
 // counter mode and dynamic shared memory of the query kernel for this index
 static void query_layout(const nq_index* ix, int& mode, size_t& smem) {
   // counters + 32 spare words (dummy targets of the branch-free count) + the kernel's static shared memory
-  const size_t spare = 128, fixed = 4096, optin = ix->ctx->smem_optin;
+  const size_t spare = 128, fixed = 26 * 1024, optin = ix->ctx->smem_optin;
   const size_t pack = (size_t)((ix->n + 1) / 2) * 4, full = (size_t)ix->n * 4;
   if (ix->p.S <= 15 && pack + spare + fixed <= optin) { mode = kPack16; smem = pack + spare; }
   else if (full + spare + fixed <= optin) { mode = kSmem32; smem = full + spare; }
@@ -432,9 +662,7 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
   // the prefetch window (kPfAhead + 1 chunks of kPfCells cells: directory rows + posting arrays) must sit in L2
   a.prefetch = (uint64_t)(kPfAhead + 1) * kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem <= (64ull << 20);
 
-  // queries per launch: everything at once unless global counters would be too large
-  uint64_t q_per_launch = nq;
-  if (mode == kGlobal32) q_per_launch = std::max<uint64_t>(1, std::min<uint64_t>(nq, (1ull << 30) / ((uint64_t)ix->n * 4)));
+  const uint64_t q_per_launch = query_wave(ix, mode, smem, a, nq);
 
   unsigned long long* d_cursor = nullptr;
   uint64_t* d_begin = nullptr;
@@ -520,5 +748,46 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
     *out = hits;
   }
   cleanup();
+  return NQ_OK;
+}
+
+// Dense rows for --matrix: d_out[q][g] = (cells where query q and genome g carry the same valid
+// fingerprint) & wrap_mask, for every genome of the shard.  Same kernels as nq_query_impl.
+int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t wrap_mask, uint32_t* d_out) {
+  if (!ix || !d_out) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  if (nq == 0) return NQ_OK;
+  nq_ctx* ctx = ix->ctx;
+  const nq_params& p = ix->p;
+  QueryArgs a{};
+  a.qsk = d_sketches; a.dir = ix->d_row; a.gids = ix->d_gids;
+  a.F = p.F; a.range = (uint32_t)p.range; a.n = ix->n; a.row_stride = ix->row_stride; a.gid_stride = ix->gid_stride;
+  a.gid_base = ix->gid_base;
+  a.wrap_mask = wrap_mask;
+  a.dense = d_out;
+  int mode;
+  size_t smem;
+  query_layout(ix, mode, smem);
+  a.prefetch = (uint64_t)(kPfAhead + 1) * kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem <= (64ull << 20);
+  const uint64_t q_per_launch = query_wave(ix, mode, smem, a, nq);
+  unsigned long long* d_cursor = nullptr;  // [1] = gather statistics
+  NQ_TRY(nq_dmalloc(ctx, (void**)&d_cursor, 16));
+  if (mode == kGlobal32) {
+    const int st = nq_dmalloc(ctx, (void**)&a.gcounts, q_per_launch * ix->n * 4);
+    if (st != NQ_OK) { nq_dfree(ctx, d_cursor); return st; }
+  }
+  a.cursor = d_cursor;
+  cudaError_t e = cudaMemsetAsync(d_cursor, 0, 16, ctx->stream);
+  {
+    NqTimer timer(ctx, NQK_MATRIX);
+    for (uint64_t q0 = 0; q0 < nq && e == cudaSuccess; q0 += q_per_launch) {
+      const unsigned nb = (unsigned)std::min<uint64_t>(q_per_launch, nq - q0);
+      e = launch_query(ix->elem, mode, smem, nb, a, q0, ctx->stream);
+      ctx->launches++;
+      if (e == cudaSuccess) e = cudaPeekAtLastError();
+    }
+  }
+  nq_dfree(ctx, d_cursor);
+  nq_dfree(ctx, a.gcounts);
+  if (e != cudaSuccess) return nq_set_error(NQ_ERR_CUDA, "matrix row kernel launch failed: %s", cudaGetErrorString(e));
   return NQ_OK;
 }

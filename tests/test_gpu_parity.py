@@ -336,6 +336,56 @@ def test_large_n_global_counter_path(nb, ctx, n):
     assert np.array_equal(ptr, ohp) and np.array_equal(c, oc) and np.array_equal(gid, og)
 
 
+def test_matrix_rows_equal_pairwise_cell_matches(nb, ctx):
+    """--matrix rows are computed as dense queries of the genomes' own (index-rebuilt) sketches:
+    check them against the definition, counts[a][b] = #cells where a and b post the same fingerprint
+    (src/niqki_index.cpp:570-598), on sketches with unposted cells, out-of-range fingerprints and clones."""
+    rng = np.random.default_rng(7)
+    n, ps = 3000, dict(K=31, S=10, W=12, H=4)
+    F = 1024
+    g = gpu_index(nb, ctx, J=0.0, **ps)
+    sks = (rng.integers(0, 4096, size=(n, F)) & rng.integers(0, 4096, size=(n, F))).astype(np.int32)
+    sks[rng.random(n) < 0.05] = sks[1]
+    sks[rng.random((n, F)) < 0.02] = -1
+    sks[rng.random((n, F)) < 0.01] = 4096 + 17
+    g.insert_sketches(sks, gid_base=0)
+    valid = (sks >= 0) & (sks < 4096)
+    for a, b in [(0, 40), (1490, 1530), (n - 7, n)]:
+        m = g.query_range(a, b, wrap16=False)
+        exp = np.stack([((sks == sks[r]) & valid & valid[r]).sum(axis=1) for r in range(a, b)]).astype(np.uint32)
+        assert np.array_equal(m, exp)
+    assert g.query_range(5, 5).shape[0] == 0
+
+
+def test_posting_index_beyond_32_bits(nb, ctx):
+    """S=18 with > 16384 genomes: F * gid_stride exceeds 2^32, the kernels switch to 64-bit posting
+    indexes.  Sketches are generated on the device; expected counts come from torch on the same tensors."""
+    import torch
+
+    n, S = 16_500, 18
+    F = 1 << S
+    g = gpu_index(nb, ctx, K=31, S=S, W=12, H=4, J=0.0)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    sk = torch.randint(0, 48, (n, F), dtype=torch.int32, device="cuda", generator=gen)
+    sk[:, ::97] = -1
+    sk[3] = sk[n - 1]
+    g.insert_sketches(sk, gid_base=0)
+    assert g.info()["n_postings"] == int((sk >= 0).sum())
+    rows = [0, 3, n - 1]
+    q = sk[rows].contiguous()
+    ptr, c, gid = g.query_sketches(q, min_score=0)
+    for i, r in enumerate(rows):
+        exp = ((sk == q[i]) & (q[i] >= 0)).sum(dim=1).cpu().numpy().astype(np.uint32)
+        seg = slice(int(ptr[i]), int(ptr[i + 1]))
+        got = np.zeros(n, np.uint32)
+        got[gid[seg]] = c[seg]
+        assert np.array_equal(got, exp)
+        m = g.query_range(r, r + 1, wrap16=True)[0]
+        assert np.array_equal(m, exp & 0xFFFF)
+    assert c[int(ptr[1])] == int((q[1] >= 0).sum()) and set(gid[int(ptr[1]):int(ptr[1]) + 2]) == {3, n - 1}
+    del sk
+
+
 def test_device_pointer_api_and_synth(nb, ctx):
     """Device-resident path (torch tensors as plain device pointers) + the synthetic generators."""
     import ctypes as C
