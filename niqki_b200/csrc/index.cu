@@ -17,6 +17,7 @@
 // column is streamed with several 64-byte loads in flight per warp; 16+ warps per SM keep the
 // serial cursor chain of the ordered sweep covered.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "device_common.cuh"
@@ -163,6 +164,130 @@ __global__ void __launch_bounds__(256) cell_sort_kernel(const uint16_t* __restri
   if (lane == 0 && posted) atomicAdd(total_postings, posted);  // `posted` is only maintained by lane 0
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Few cells, many entries (reads as entries: --indexlines at S = 8 has 256 cells and millions of
+// ids): one warp per cell leaves the machine empty, so the cell's column is cut into chunks of
+// kChunk entries and the counting sort becomes three kernels over (cell, chunk) tasks —
+//   A. chunk_hist_kernel:    per-task histogram of the W-bit keys           -> H[task][bin]
+//   B. chunk_scan_kernel:    per cell, bin-major / chunk-minor exclusive scan -> directory row,
+//                            H[task][bin] becomes the task's first slot of list `bin`
+//   C. chunk_scatter_kernel: per task, the ordered scatter of cell_sort_kernel from those cursors
+// (lists stay gid-ascending because chunks are gid ranges and the scatter inside one is stable).
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kChunk = 65536;
+
+__global__ void __launch_bounds__(256) chunk_hist_kernel(const uint16_t* __restrict__ fpT, uint32_t n_pad, uint32_t range,
+                                                         uint32_t chunks, uint64_t tasks, uint32_t* __restrict__ H) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t* cnt = smem + (size_t)warp * range;
+  constexpr int U = 8;
+  for (uint64_t task = (uint64_t)blockIdx.x * nw + warp; task < tasks; task += (uint64_t)gridDim.x * nw) {
+    const uint32_t cell = (uint32_t)(task / chunks), chunk = (uint32_t)(task % chunks);
+    const uint16_t* col = fpT + (size_t)cell * n_pad;
+    const uint32_t g_begin = chunk * kChunk, g_end = min(n_pad, g_begin + kChunk);
+    for (uint32_t i = lane; i < range; i += 32) cnt[i] = 0;
+    __syncwarp();
+    for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32 * U) {
+      uint16_t fp[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) fp[u] = g0 + u * 32 < g_end ? col[g0 + u * 32 + lane] : kNoPost;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (fp[u] != kNoPost) atomicAdd(&cnt[fp[u]], 1u);
+    }
+    __syncwarp();
+    uint32_t* h = H + task * range;
+    for (uint32_t i = lane; i < range; i += 32) h[i] = cnt[i];
+    __syncwarp();
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) chunk_scan_kernel(uint32_t* __restrict__ H, uint32_t range, uint32_t chunks,
+                                                        uint2* __restrict__ dir, uint32_t row_stride,
+                                                        unsigned long long* __restrict__ total_postings) {
+  extern __shared__ __align__(16) uint32_t s_tot[];  // [range] list sizes, then list begins
+  __shared__ uint32_t s_warp[NT / 32];
+  const uint32_t cell = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* h = H + (size_t)cell * chunks * range;
+  for (uint32_t bin = tid; bin < range; bin += NT) {  // chunk-minor running sums, coalesced over bins
+    uint32_t run = 0;
+    for (uint32_t c = 0; c < chunks; ++c) {
+      const uint32_t v = h[(size_t)c * range + bin];
+      h[(size_t)c * range + bin] = run;
+      run += v;
+    }
+    s_tot[bin] = run;
+  }
+  __syncthreads();
+  // exclusive scan over the bins: every thread owns `per` consecutive bins
+  const uint32_t per = (range + NT - 1) / NT, b0 = tid * per, b1 = min(range, b0 + per);
+  uint32_t mine = 0;
+  for (uint32_t b = b0; b < b1; ++b) mine += s_tot[b];
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t before = incl - mine;
+  for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
+  uint2* myrow = dir + (size_t)cell * row_stride;
+  for (uint32_t b = b0; b < b1; ++b) {
+    const uint32_t c = s_tot[b];
+    myrow[b] = make_uint2(before, before + c);
+    s_tot[b] = before;
+    before += c;
+  }
+  if (tid == NT - 1 && before) atomicAdd(total_postings, (unsigned long long)before);
+  __syncthreads();
+  for (uint32_t bin = tid; bin < range; bin += NT) {
+    const uint32_t base = s_tot[bin];
+    for (uint32_t c = 0; c < chunks; ++c) h[(size_t)c * range + bin] += base;
+  }
+}
+
+__global__ void __launch_bounds__(256) chunk_scatter_kernel(const uint16_t* __restrict__ fpT, uint32_t n_pad, uint32_t range,
+                                                            uint32_t chunks, uint64_t tasks, const uint32_t* __restrict__ H,
+                                                            uint32_t* __restrict__ gids, uint32_t gid_stride) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t* cur = smem + (size_t)warp * range;
+  constexpr unsigned kFull = 0xFFFFFFFFu;
+  const unsigned lt = (1u << lane) - 1;
+  constexpr int U = 8;
+  for (uint64_t task = (uint64_t)blockIdx.x * nw + warp; task < tasks; task += (uint64_t)gridDim.x * nw) {
+    const uint32_t cell = (uint32_t)(task / chunks), chunk = (uint32_t)(task % chunks);
+    const uint16_t* col = fpT + (size_t)cell * n_pad;
+    const uint32_t g_begin = chunk * kChunk, g_end = min(n_pad, g_begin + kChunk);
+    const uint32_t* h = H + task * range;
+    for (uint32_t i = lane; i < range; i += 32) cur[i] = h[i];
+    __syncwarp();
+    uint32_t* out = gids + (size_t)cell * gid_stride;
+    for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32 * U) {
+      uint16_t fp[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) fp[u] = g0 + u * 32 < g_end ? col[g0 + u * 32 + lane] : kNoPost;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (g0 + u * 32 >= g_end) break;
+        const bool valid = fp[u] != kNoPost;
+        const unsigned same = __match_any_sync(kFull, fp[u]);
+        const uint32_t rank = __popc(same & lt);
+        const uint32_t base = valid ? cur[fp[u]] : 0;
+        __syncwarp();
+        if (valid && rank == 0) cur[fp[u]] = base + __popc(same);
+        __syncwarp();
+        if (valid) out[base + rank] = g0 + u * 32 + lane;
+      }
+    }
+    __syncwarp();
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // Compact form (n <= kMaxCompact, u16 ids): one CTA per cell, everything in shared memory.
@@ -371,9 +496,46 @@ __global__ void __launch_bounds__(NT) cell_build_kernel(const uint16_t* __restri
   if (tid == 0 && posted) atomicAdd(total_postings, (unsigned long long)posted);
 }
 
+
+// ---- split16 side arrays (internal.h): u16 copy of the postings + {begin, mid, end} directory -------
+__global__ void split16_gids_kernel(const uint32_t* __restrict__ g32, uint16_t* __restrict__ g16, size_t count) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+    g16[i] = (uint16_t)g32[i];
+}
+__global__ void split16_dir_kernel(const uint2* __restrict__ dir, const uint32_t* __restrict__ g32, uint4* __restrict__ dir3,
+                                   uint32_t row_stride, uint32_t gid_stride, size_t entries) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < entries; i += (size_t)gridDim.x * blockDim.x) {
+    const uint2 w = dir[i];
+    const uint32_t* g = g32 + (i / row_stride) * gid_stride;
+    uint32_t lo = w.x, hi = w.y;  // first posting >= 65536 in the gid-sorted list [w.x, w.y)
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (g[mid] < 65536u) lo = mid + 1; else hi = mid;
+    }
+    dir3[i] = make_uint4(w.x, lo, w.y, 0u);
+  }
+}
+
 }  // namespace nq
 
 using namespace nq;
+
+int nq_index_make_split16(nq_index* ix) {
+  static const char* env = getenv("NQ_SPLIT16");  // "0": keep the u32 gather (measurement only)
+  // below 65600 genomes the dummy ids of the query kernel (just above n) would not be >= 2^16
+  if (ix->elem != 4 || ix->n < 65600u || ix->n > 131072u || ix->p.S > 15 || (env && env[0] == '0')) return NQ_OK;
+  nq_ctx* ctx = ix->ctx;
+  const size_t entries = (size_t)ix->p.F * ix->row_stride, count = (size_t)ix->p.F * ix->gid_stride;
+  NQ_TRY(nq_dmalloc(ctx, (void**)&ix->d_dir3, entries * sizeof(uint4)));
+  NQ_TRY(nq_dmalloc(ctx, (void**)&ix->d_gids16, (count + kQuerySlack) * sizeof(uint16_t)));
+  split16_gids_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(static_cast<const uint32_t*>(ix->d_gids), ix->d_gids16, count);
+  NQ_CHECK_LAUNCH(ctx);
+  split16_dir_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(static_cast<const uint2*>(ix->d_row),
+                                                                  static_cast<const uint32_t*>(ix->d_gids), ix->d_dir3,
+                                                                  ix->row_stride, ix->gid_stride, entries);
+  NQ_CHECK_LAUNCH(ctx);
+  return NQ_OK;
+}
 
 template <typename IT>
 static cudaError_t launch_cell_sort(nq_ctx* ctx, const uint16_t* d_fpT, uint32_t n, uint32_t n_pad, nq_index* ix,
@@ -393,6 +555,39 @@ static cudaError_t launch_cell_sort(nq_ctx* ctx, const uint16_t* d_fpT, uint32_t
                                                             ix->row_stride, static_cast<IT*>(ix->d_gids), ix->gid_stride,
                                                             d_total);
   ctx->launches++;
+  return cudaPeekAtLastError();
+}
+
+// u32 ids with few cells: the (cell, chunk) counting sort.  Returns cudaErrorInvalidValue when it does not apply.
+static cudaError_t launch_chunked_sort(nq_ctx* ctx, const uint16_t* d_fpT, uint32_t n_pad, nq_index* ix,
+                                       unsigned long long* d_total) {
+  const uint32_t range = (uint32_t)ix->p.range, F = ix->p.F;
+  const uint32_t chunks = (n_pad + kChunk - 1) / kChunk;
+  const uint64_t tasks = (uint64_t)F * chunks;
+  // worth it only when one warp per cell cannot fill the SMs and there is more than one chunk
+  if (ix->elem != 4 || chunks < 2 || F >= (uint32_t)ctx->sm_count * 16 || tasks * range * 4 > (8ull << 30))
+    return cudaErrorInvalidValue;
+  const uint32_t nw = 8;
+  const size_t smem = (size_t)range * 4 * nw;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(chunk_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(chunk_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(chunk_scan_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)range * 4)) != cudaSuccess)
+    return e;
+  uint32_t* d_H = nullptr;
+  if (nq_dmalloc(ctx, (void**)&d_H, tasks * range * 4) != NQ_OK) return cudaErrorMemoryAllocation;
+  const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (ctx->smem_optin + 1024) / (smem + 1024)));
+  const uint32_t grid = (uint32_t)std::min<uint64_t>((tasks + nw - 1) / nw, (uint64_t)ctx->sm_count * per_sm);
+  {
+    NqTimer timer(ctx, NQK_CELLSORT);
+    chunk_hist_kernel<<<grid, nw * 32, smem, ctx->stream>>>(d_fpT, n_pad, range, chunks, tasks, d_H);
+    chunk_scan_kernel<1024><<<F, 1024, (size_t)range * 4, ctx->stream>>>(d_H, range, chunks, static_cast<uint2*>(ix->d_row),
+                                                                        ix->row_stride, d_total);
+    chunk_scatter_kernel<<<grid, nw * 32, smem, ctx->stream>>>(d_fpT, n_pad, range, chunks, tasks, d_H,
+                                                               static_cast<uint32_t*>(ix->d_gids), ix->gid_stride);
+  }
+  ctx->launches += 3;
+  nq_dfree(ctx, d_H);
   return cudaPeekAtLastError();
 }
 
@@ -464,6 +659,7 @@ int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketch
   ctx->launches++;
   e = cudaErrorInvalidValue;
   if (ix->elem == 2) e = launch_cell_build(ctx, d_fpT, n, n_pad, ix, d_total);
+  if (e == cudaErrorInvalidValue) e = launch_chunked_sort(ctx, d_fpT, n_pad, ix, d_total);  // few cells, many entries
   if (e == cudaErrorInvalidValue)  // u32 ids, or a cell that does not fit in shared memory: one warp per cell
     e = ix->elem == 2 ? launch_cell_sort<uint16_t>(ctx, d_fpT, n, n_pad, ix, d_total)
                       : launch_cell_sort<uint32_t>(ctx, d_fpT, n, n_pad, ix, d_total);
@@ -476,7 +672,7 @@ int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketch
   nq_dfree(ctx, d_fpT);
   nq_dfree(ctx, d_total);
   d_fpT = nullptr; d_total = nullptr;
-  if ((st = nq_query_prepare(ix)) != NQ_OK) return fail(st);
+  if ((st = nq_index_make_split16(ix)) != NQ_OK || (st = nq_query_prepare(ix)) != NQ_OK) return fail(st);
   *out = ix;
   return NQ_OK;
 }
@@ -487,6 +683,8 @@ extern "C" int nq_index_free(nq_index* ix) {
     cudaSetDevice(ix->ctx->device);
     nq_dfree(ix->ctx, ix->d_row);
     nq_dfree(ix->ctx, ix->d_gids);
+    nq_dfree(ix->ctx, ix->d_dir3);
+    nq_dfree(ix->ctx, ix->d_gids16);
     nq_dfree(ix->ctx, ix->d_pool);
   }
   delete ix;
@@ -499,7 +697,9 @@ extern "C" int nq_index_info(const nq_index* ix, uint64_t* n_postings, uint32_t*
   if (n_postings) *n_postings = ix->n_postings;
   if (n_genomes) *n_genomes = ix->n;
   if (gid_base) *gid_base = ix->gid_base;
-  if (device_bytes) *device_bytes = (uint64_t)ix->p.F * (2ull * ix->row_stride + ix->gid_stride) * ix->elem;
+  if (device_bytes)
+    *device_bytes = (uint64_t)ix->p.F * (2ull * ix->row_stride + ix->gid_stride) * ix->elem +
+                    (ix->d_dir3 ? (uint64_t)ix->p.F * (16ull * ix->row_stride + 2ull * ix->gid_stride) : 0);
   return NQ_OK;
 }
 
@@ -583,6 +783,7 @@ static int import_t(nq_index* ix, const uint32_t* list_sizes, const uint32_t* gi
       (e = cudaMemcpyAsync(ix->d_gids, hg.data(), hg.size() * sizeof(IT), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
       (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
     return nq_set_error(NQ_ERR_CUDA, "index import failed: %s", cudaGetErrorString(e));
+  NQ_TRY(nq_index_make_split16(ix));
   return nq_query_prepare(ix);
 }
 

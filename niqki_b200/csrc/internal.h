@@ -101,6 +101,11 @@ struct nq_index {
   uint32_t gid_stride = 0;  // elements per cell in d_gids: n rounded up to 32 bytes
   void* d_row = nullptr;    // directory [F][row_stride] of packed {begin,end}: u32 (elem 2) or uint2 (elem 4)
   void* d_gids = nullptr;   // [F][gid_stride] + kQuerySlack elements
+  // split16 side arrays (65400 < n <= 131072 only): the same postings as u16 (gid & 0xFFFF; lists are
+  // gid-sorted, so each list is a run of ids < 65536 followed by a run of ids >= 65536) and a directory
+  // {begin, mid, end, 0} with mid = first posting >= 65536.  Halves the bytes the query kernel gathers.
+  uint4* d_dir3 = nullptr;       // [F][row_stride]
+  uint16_t* d_gids16 = nullptr;  // [F][gid_stride] + kQuerySlack
   // device-resident results of the last nq_query_batch_device(out == NULL)
   uint64_t* d_pool = nullptr;
   uint64_t pool_cap = 0;
@@ -116,6 +121,7 @@ int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketch
 constexpr uint32_t kMaxCompact = 65400;  // genomes per shard in the u16 form (leaves room for the query kernel's dummy ids)
 constexpr uint32_t kQuerySlack = 64;     // elements reserved behind d_gids[F][gid_stride]
 int nq_query_prepare(nq_index* ix);      // fills that slack; call once the index arrays exist
+int nq_index_make_split16(nq_index* ix);  // index.cu: builds d_dir3 / d_gids16 when the shard size calls for them
 int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t min_score, nq_hits** out);
 int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t wrap_mask, uint32_t* d_out);
 int nq_matrix_impl(nq_index* ix, uint32_t row_begin, uint32_t row_end, int wrap16, uint32_t* h_counts);

@@ -41,17 +41,21 @@ struct QueryArgs {
   uint64_t* hit_begin;  // [nq]
   uint32_t* hit_n;      // [nq]
   uint32_t* gcounts;    // global counters [gridDim.x][n] (GLOBAL mode only)
+  uint32_t parts;       // GLOBAL mode, segment-table form: gridDim.y CTAs share one query (counters zeroed before, finished after)
   uint32_t prefetch;    // cooperative L2 prefetch of upcoming cells (only when a few chunks of cells fit in L2)
+  const uint4* dir3;       // split16 side arrays of the index (internal.h), or null
+  const uint16_t* gids16;
+  uint64_t q_end;       // one past the last query of the launch (kDual16: a CTA's second query may not exist)
   uint32_t* dense;      // when set: row q of [nq][n] takes every genome's count instead of the thresholded hit list (--matrix)
 };
 
-enum CountMode { kPack16 = 0, kSmem32 = 1, kGlobal32 = 2 };
+enum CountMode { kPack16 = 0, kSmem32 = 1, kGlobal32 = 2, kDual16 = 3 };
 
 // id carried by stream slots past the end of a group's stream: lands in spare counter word `lane`
 // (shared-memory modes) or is skipped (global mode).  Must fit IT: n <= kMaxCompact in the u16 form.
 template <typename IT>
 __host__ __device__ __forceinline__ uint32_t query_dummy_id(int mode, uint32_t words, uint32_t lane) {
-  return mode == kPack16 ? 2 * (words + lane) : mode == kSmem32 ? words + lane : (uint32_t)(IT)0xFFFFFFFFu;
+  return mode == kPack16 ? 2 * (words + lane) : (mode == kSmem32 || mode == kDual16) ? words + lane : (uint32_t)(IT)0xFFFFFFFFu;
 }
 
 // Every load of the gather loop is UNCONDITIONAL (dead lanes read a harmless location and their
@@ -67,6 +71,8 @@ struct DirWord<uint16_t> {
   uint32_t w;
   __device__ __forceinline__ void clear() { w = 0; }
   __device__ __forceinline__ void load(const void* dir, size_t at) { w = __ldg(static_cast<const uint32_t*>(dir) + at); }
+  __device__ __forceinline__ void load32(const void* dir, uint32_t at) { w = __ldg(static_cast<const uint32_t*>(dir) + at); }
+  __device__ __forceinline__ uint32_t mid() const { return 0; }
   __device__ __forceinline__ uint32_t begin() const { return w & 0xFFFFu; }
   __device__ __forceinline__ uint32_t end() const { return w >> 16; }
 };
@@ -78,8 +84,25 @@ struct DirWord<uint32_t> {
     const uint2 v = __ldg(static_cast<const uint2*>(dir) + at);
     x = v.x; y = v.y;
   }
+  __device__ __forceinline__ void load32(const void* dir, uint32_t at) {
+    const uint2 v = __ldg(static_cast<const uint2*>(dir) + at);
+    x = v.x; y = v.y;
+  }
+  __device__ __forceinline__ uint32_t mid() const { return 0; }
   __device__ __forceinline__ uint32_t begin() const { return x; }
   __device__ __forceinline__ uint32_t end() const { return y; }
+};
+
+// split16 directory entry {begin, mid, end, 0}
+struct DirWord3 {
+  uint32_t x, y, z;
+  __device__ __forceinline__ void load32(const void* dir, uint32_t at) {
+    const uint4 v = __ldg(static_cast<const uint4*>(dir) + at);
+    x = v.x; y = v.y; z = v.z;
+  }
+  __device__ __forceinline__ uint32_t begin() const { return x; }
+  __device__ __forceinline__ uint32_t mid() const { return y; }
+  __device__ __forceinline__ uint32_t end() const { return z; }
 };
 
 // clamped shift: PTX shl.b32 yields 0 for shift amounts >= 32 (C++ leaves that undefined)
@@ -136,7 +159,8 @@ __device__ __forceinline__ void prefetch_chunk(const QueryArgs& a, const PfSlice
 // ---- threshold (:661-665) + compaction, shared by both gather forms: count the hits, reserve a pool
 // segment with one atomicAdd, then write (count, gid) in gid order
 template <int MODE, int NT>
-__device__ __forceinline__ void query_finish(const QueryArgs& a, uint64_t q, const uint32_t* cnt, uint32_t gathered) {
+__device__ __forceinline__ void query_finish(const QueryArgs& a, uint64_t q, const uint32_t* cnt, uint32_t gathered,
+                                             uint32_t shift) {
   __shared__ uint32_t s_warp[NT / 32];
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_total;
@@ -145,6 +169,7 @@ __device__ __forceinline__ void query_finish(const QueryArgs& a, uint64_t q, con
   auto count_of = [&](uint32_t g) -> uint32_t {
     uint32_t c;
     if (MODE == kPack16) c = (cnt[g >> 1] >> ((g & 1) * 16)) & 0xFFFFu;
+    else if (MODE == kDual16) c = (cnt[g] >> shift) & 0xFFFFu;
     else if (MODE == kGlobal32) c = __ldcg(&cnt[g]);
     else c = cnt[g];
     return c & a.wrap_mask;
@@ -360,7 +385,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 9 : 1) query_count_kernel(Quer
     if ((uint32_t)d != phase) drain(lbuf[d], live[d]);
   __syncthreads();
 
-  query_finish<MODE, NT>(a, q, cnt, gathered);
+  query_finish<MODE, NT>(a, q, cnt, gathered, 0);
 }
 
 // ---- segment-table form --------------------------------------------------------------------------
@@ -382,15 +407,37 @@ struct SegRef {
   int32_t rem;  // postings of the list from there on (lanes at or past it are dead)
 };
 
-template <typename IT, int MODE, int NT, typename IDX, int SEG, int T, int R>
-__global__ void __launch_bounds__(NT, NT == 128 ? 8 : 1) query_count_seg_kernel(QueryArgs a, uint64_t q0) {
+// MODE kDual16 (small shards, S <= 15): the CTA counts TWO queries, warps [0, NW/2) the first and
+// [NW/2, NW) the second, into one u32 word per genome — the first query owns the low half-word, the
+// second the high one (a count never exceeds F <= 32768, so the low half cannot carry).  Counting a
+// posting is then `atomicAdd(&cnt[id], inc)` with a per-warp constant: shift + ATOMS instead of the
+// five ALU instructions that pick the half-word of a packed pair.
+// D = batches in the register ring: the batch gathered D-1 batches ago is counted while the newer
+// ones fly (D = 3 for the 128/256-thread forms: with D = 2 only one batch's issue time, less than
+// an L2 hit, lies between a gather and its use — 31 % of the stall samples in r01 ncu).
+// SPLIT (shards of 65.6k..131k genomes, SEG = 32, packed counters): postings come from the u16 copy
+// `gids16` and the directory from `dir3` {begin, mid, end}: ids from position `mid` of a list on
+// are >= 65536 and get the 2^16 back when they are counted.  Which lanes of a round lie past `mid`
+// is known at gather time only, so one bit per round is kept beside each ring slot (`hmask`).  A
+// segment descriptor carries {postings left, min(postings left, ids below 2^16 left)} as two
+// half-words: lanes at or past the second number are "high", which includes the dead lanes of a
+// list's last round — their dummy id is stored minus 2^16.
+template <typename IT, int MODE, int NT, typename IDX, int SEG, int T, int R, int D, bool SPLIT = false>
+__global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : 1) query_count_seg_kernel(QueryArgs a, uint64_t q0) {
+  static_assert(!SPLIT || (SEG == 32 && MODE == kPack16 && sizeof(IT) == 2 && sizeof(IDX) == 4), "split16 form");
   constexpr int SPR = 32 / SEG;  // segments per round
+  constexpr bool DUAL = MODE == kDual16;
+  constexpr int NW = NT / 32, NWQ = DUAL ? NW / 2 : NW;  // warps per query
   static_assert(SEG == 8 || SEG == 16 || SEG == 32, "segment size");
   static_assert(T % SPR == 0, "table = whole rounds");
+  static_assert(D >= 2 && D <= 4, "ring depth");
   extern __shared__ __align__(16) uint32_t smem[];
-  __shared__ __align__(16) SegRef<IDX> s_tab[NT / 32][T + SPR];
-  const uint64_t q = q0 + blockIdx.x;
+  __shared__ __align__(16) SegRef<IDX> s_tab[NW][T + SPR];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t half = DUAL ? warp / NWQ : 0, qwarp = DUAL ? warp % NWQ : warp;
+  const uint64_t qbase = q0 + (uint64_t)blockIdx.x * (DUAL ? 2 : 1);
+  const uint64_t q = qbase + half;
+  const bool have_q = !DUAL || q < a.q_end;
   uint32_t* cnt = MODE == kGlobal32 ? a.gcounts + (size_t)blockIdx.x * a.n : smem;
   const uint32_t words = MODE == kPack16 ? (a.n + 1) / 2 : a.n;
   constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -400,71 +447,123 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 1) query_count_seg_kernel(
     pf = make_pf_slice(a, sizeof(IT), lane);
     for (uint32_t ch = 0; ch < kPfAhead; ++ch) prefetch_chunk(a, pf, ch);
   }
-  for (uint32_t i = tid; i < words; i += NT) cnt[i] = 0;
+  const bool shared_q = MODE == kGlobal32 && a.parts != 0;  // counters zeroed by the host, finished by query_finish_kernel
+  if (!shared_q)
+    for (uint32_t i = tid; i < words; i += NT) cnt[i] = 0;
   __syncthreads();
 
-  const int32_t* sk = a.qsk + q * a.F;
-  const IT* gids = static_cast<const IT*>(a.gids);
+  const int32_t* sk = a.qsk + (have_q ? q : qbase) * a.F;
+  const IT* gids = SPLIT ? reinterpret_cast<const IT*>(a.gids16) : static_cast<const IT*>(a.gids);
   SegRef<IDX>* tab = s_tab[warp];
   const uint32_t sub = lane & (SEG - 1), grp = lane / SEG;
   uint32_t gathered = 0;
   const uint32_t dummy = query_dummy_id<IT>(MODE, words, lane);
-  const IDX dead_at = (IDX)a.F * a.gid_stride + lane;
+  const IDX dead_at = (IDX)a.F * a.gid_stride + (DUAL ? 32 : 0) + lane;
+  const uint32_t inc = half ? 0x10000u : 1u;
   auto count = [&](uint32_t l) {
-    if (MODE == kPack16) atomicAdd(&smem[l >> 1], (l & 1) * 0xFFFFu + 1u);
+    if (DUAL) atomicAdd(&smem[l], inc);
+    else if (MODE == kPack16) atomicAdd(&smem[l >> 1], (l & 1) * 0xFFFFu + 1u);
     else if (MODE == kSmem32) atomicAdd(&smem[l], 1u);
     else if (l != dummy) atomicAdd(&cnt[l], 1u);
   };
-  const uint32_t step = NT;
-  uint32_t c_cur = warp * 32;
+  // Cells per sweep.  GLOBAL mode with `parts`: the gridDim.y CTAs of a query form one pool of
+  // virtual warps; with more warps than groups of 32 cells (reads as entries: 256 cells, lists of
+  // 10^5 postings) every list is cut into `pieces` and a warp takes one piece of its group's lists.
+  uint32_t step = NWQ * 32, c_cur = qwarp * 32, piece = 0, pieces = 1;
+  uint32_t F = have_q ? a.F : 0;  // a CTA's missing second query walks no cells
+  if (MODE == kGlobal32 && a.parts) {
+    const uint32_t vw = blockIdx.y * NW + warp, VW = gridDim.y * NW, ngroups = (a.F + 31) / 32;
+    if (VW <= ngroups) {
+      c_cur = vw * 32; step = VW * 32;
+    } else {
+      pieces = VW / ngroups; piece = vw / ngroups;
+      c_cur = (vw % ngroups) * 32; step = ngroups * 32;  // one group per warp
+      if (piece >= pieces) F = 0;
+    }
+  }
   uint32_t fp_next = 0xFFFFFFFFu, fp_next2 = 0xFFFFFFFFu;
-  if (c_cur + step + lane < a.F) fp_next = (uint32_t)__ldg(&sk[c_cur + step + lane]);
-  auto probe = [&](DirWord<IT>& d, uint32_t cell, uint32_t fp) {
-    d.load(a.dir, (size_t)min(cell, a.F - 1) * a.row_stride + min(fp, a.range - 1));
+  if (c_cur + step + lane < F) fp_next = (uint32_t)__ldg(&sk[c_cur + step + lane]);
+  // directory probe with 32-bit element indexes (the host checks F * row_stride < 2^32)
+  typedef typename std::conditional<SPLIT, DirWord3, DirWord<IT>>::type DW;
+  auto probe = [&](DW& d, uint32_t cell, uint32_t fp) {
+    d.load32(SPLIT ? static_cast<const void*>(a.dir3) : a.dir, min(cell, a.F - 1) * a.row_stride + min(fp, a.range - 1));
   };
-  DirWord<IT> dw, dw_next;
+  DW dw, dw_next;
   uint32_t fp_cur = 0xFFFFFFFFu;
-  if (c_cur + lane < a.F) fp_cur = (uint32_t)__ldg(&sk[c_cur + lane]);
+  if (c_cur + lane < F) fp_cur = (uint32_t)__ldg(&sk[c_cur + lane]);
   probe(dw, c_cur + lane, fp_cur);
 
-  uint32_t lbuf[2][R];
-  uint32_t live0 = 0, live1 = 0;
+  uint32_t lbuf[D][R];
+  uint32_t live[D], hmask[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) live[d] = hmask[d] = 0;
   uint32_t phase = 0;
-  auto drain = [&](uint32_t (&l)[R], uint32_t nl) {
+  auto drain = [&](uint32_t (&l)[R], uint32_t hm, uint32_t nl) {
     if (nl >= (uint32_t)R) {
 #pragma unroll
-      for (int k = 0; k < R; ++k) count(l[k]);
+      for (int k = 0; k < R; ++k) count(SPLIT ? l[k] + (((hm >> k) & 1u) << 16) : l[k]);
     } else {
 #pragma unroll
       for (int k = 0; k < R - 1; ++k)
-        if ((uint32_t)k < nl) count(l[k]);
+        if ((uint32_t)k < nl) count(SPLIT ? l[k] + (((hm >> k) & 1u) << 16) : l[k]);
+    }
+  };
+  auto gather_round = [&](uint32_t& dst, uint32_t& hm, const SegRef<IDX>* t, int k) {
+    const SegRef<IDX> d = t[k * SPR + grp];
+    if (SPLIT) {
+      const uint32_t rem = (uint32_t)d.rem & 0xFFFFu, below = (uint32_t)d.rem >> 16;
+      dst = gids[sub < rem ? d.at + sub : dead_at];
+      hm |= (sub >= below ? 1u : 0u) << k;
+    } else {
+      dst = gids[(int32_t)sub < d.rem ? d.at + sub : dead_at];
     }
   };
   // gather nb (1..R, warp-uniform) rounds starting at table position t0 (a multiple of SPR)
-  auto gather = [&](uint32_t (&l)[R], const SegRef<IDX>* t0, uint32_t nb) {
+  auto gather = [&](uint32_t (&l)[R], uint32_t& hm, const SegRef<IDX>* t0, uint32_t nb) {
+    hm = 0;
     if (nb >= (uint32_t)R) {
 #pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const SegRef<IDX> d = t0[k * SPR + grp];
-        l[k] = gids[(int32_t)sub < d.rem ? d.at + sub : dead_at];
-      }
+      for (int k = 0; k < R; ++k) gather_round(l[k], hm, t0, k);
     } else {
 #pragma unroll
       for (int k = 0; k < R - 1; ++k)
-        if ((uint32_t)k < nb) {
-          const SegRef<IDX> d = t0[k * SPR + grp];
-          l[k] = gids[(int32_t)sub < d.rem ? d.at + sub : dead_at];
-        }
+        if ((uint32_t)k < nb) gather_round(l[k], hm, t0, k);
     }
   };
-  for (; c_cur < a.F; c_cur += step) {
+  // one batch: fill ring slot `phase`, count the oldest slot (phase+1 mod D, filled D-1 batches ago)
+  auto batch = [&](const SegRef<IDX>* t0, uint32_t nb) {
+#pragma unroll
+    for (int p = 0; p < D; ++p)
+      if (phase == (uint32_t)p) {
+        gather(lbuf[p], hmask[p], t0, nb);
+        drain(lbuf[(p + 1) % D], hmask[(p + 1) % D], live[(p + 1) % D]);
+        live[(p + 1) % D] = 0;
+        live[p] = nb;
+      }
+    phase = phase + 1 == (uint32_t)D ? 0 : phase + 1;
+  };
+  for (; c_cur < F; c_cur += step) {
     const uint32_t cell = c_cur + lane;
     if (warp == 0 && a.prefetch && c_cur % kPfCells == 0) prefetch_chunk(a, pf, c_cur / kPfCells + kPfAhead);
     fp_next2 = 0xFFFFFFFFu;
-    if (c_cur + 2 * step + lane < a.F) fp_next2 = (uint32_t)__ldg(&sk[c_cur + 2 * step + lane]);
+    if (c_cur + 2 * step + lane < F) fp_next2 = (uint32_t)__ldg(&sk[c_cur + 2 * step + lane]);
     probe(dw_next, cell + step, fp_next);
 
-    const uint32_t b = dw.begin(), len = fp_cur < a.range ? dw.end() - b : 0u;
+    uint32_t b = dw.begin(), len = fp_cur < a.range ? dw.end() - b : 0u;
+    if (MODE == kGlobal32 && pieces > 1) {  // this warp's piece of the list
+      const uint32_t lo = (uint32_t)((uint64_t)len * piece / pieces), hi = (uint32_t)((uint64_t)len * (piece + 1) / pieces);
+      b += lo; len = hi - lo;
+    }
+    const uint32_t low = SPLIT ? dw.mid() - b : 0u;  // ids below 2^16 at the head of the list
+    // descriptor of the segment that starts k postings into the list
+    auto seg_ref = [&](IDX at, uint32_t k) {
+      if constexpr (!SPLIT) {
+        return SegRef<IDX>{at, (int32_t)(len - k)};
+      } else {
+        const uint32_t rem = min(len - k, 0xFFFFu), below = low > k ? min(low - k, rem) : 0u;
+        return SegRef<IDX>{at, (int32_t)(rem | (below << 16))};
+      }
+    };
     const uint32_t nseg = (len + SEG - 1) / SEG;
     uint32_t incl = nseg;
 #pragma unroll
@@ -477,34 +576,69 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : 1) query_count_seg_kernel(
     const IDX first = (IDX)cell * a.gid_stride + b;
     gathered += len;
 
-    for (uint32_t w0 = 0; w0 < total; w0 += T) {  // windows of T segments
-      const uint32_t nwin = min((uint32_t)T, total - w0);
-      // this lane's segments that fall into the window
-      const uint32_t lo = max(excl, w0), hi = min(incl, w0 + T);
-      for (uint32_t sg = lo; sg < hi; ++sg) {
-        const uint32_t k = (sg - excl) * SEG;
-        tab[sg - w0] = SegRef<IDX>{(IDX)(first + k), (int32_t)(len - k)};
-      }
-      if (SPR > 1 && lane < SPR) tab[nwin + lane] = SegRef<IDX>{0, 0};  // dead slots of the last round
+    if (total <= (uint32_t)T) {
+      // the whole group fits the table (the usual case): straight-line stores for the first two
+      // segments of a list, a loop only for longer ones
+      if (nseg) tab[excl] = seg_ref(first, 0);
+      if (nseg > 1) tab[excl + 1] = seg_ref((IDX)(first + SEG), SEG);
+#pragma unroll 1
+      for (uint32_t sg = 2; sg < nseg; ++sg) tab[excl + sg] = seg_ref((IDX)(first + sg * SEG), sg * SEG);
+      if (SPR > 1 && lane < SPR) tab[total + lane] = SegRef<IDX>{0, 0};  // dead slots of the last round
       __syncwarp();
-      const uint32_t rounds = (nwin + SPR - 1) / SPR;
-      for (uint32_t r0 = 0; r0 < rounds; r0 += R) {
-        const uint32_t nb = min((uint32_t)R, rounds - r0);
-        // fill buffer `phase`, count the other one (gathered one batch ago, maybe by the previous group)
-        if (phase == 0) { gather(lbuf[0], tab + r0 * SPR, nb); drain(lbuf[1], live1); live0 = nb; }
-        else { gather(lbuf[1], tab + r0 * SPR, nb); drain(lbuf[0], live0); live1 = nb; }
-        phase ^= 1;
+      const uint32_t rounds = (total + SPR - 1) / SPR;
+      uint32_t r0 = 0;
+      for (; r0 + R <= rounds; r0 += R) batch(tab + r0 * SPR, R);
+      if (r0 < rounds) batch(tab + r0 * SPR, rounds - r0);
+      __syncwarp();  // the table is rewritten by the next group
+    } else {
+      for (uint32_t w0 = 0; w0 < total; w0 += T) {  // windows of T segments
+        const uint32_t nwin = min((uint32_t)T, total - w0);
+        const uint32_t lo = max(excl, w0), hi = min(incl, w0 + T);  // this lane's segments inside the window
+#pragma unroll 1
+        for (uint32_t sg = lo; sg < hi; ++sg) {
+          const uint32_t k = (sg - excl) * SEG;
+          tab[sg - w0] = seg_ref((IDX)(first + k), k);
+        }
+        if (SPR > 1 && lane < SPR) tab[nwin + lane] = SegRef<IDX>{0, 0};
+        __syncwarp();
+        const uint32_t rounds = (nwin + SPR - 1) / SPR;
+        for (uint32_t r0 = 0; r0 < rounds; r0 += R) batch(tab + r0 * SPR, min((uint32_t)R, rounds - r0));
+        __syncwarp();
       }
-      __syncwarp();  // the table is rewritten by the next window / group
     }
     dw = dw_next;
     fp_cur = fp_next;
     fp_next = fp_next2;
   }
-  if (phase == 0) drain(lbuf[1], live1);
-  else drain(lbuf[0], live0);
+  // the D-1 batches still in flight, oldest first
+#pragma unroll
+  for (int i = 1; i < D; ++i) {
+#pragma unroll
+    for (int p = 0; p < D; ++p)
+      if (phase == (uint32_t)p) drain(lbuf[(p + i) % D], hmask[(p + i) % D], live[(p + i) % D]);
+  }
   __syncthreads();
-  query_finish<MODE, NT>(a, q, cnt, gathered);
+  if (shared_q) {  // only the gather statistics; the counters are complete when the whole grid is
+#pragma unroll
+    for (int d = 16; d; d >>= 1) gathered += __shfl_xor_sync(kFull, gathered, d);
+    if (lane == 0 && gathered) atomicAdd(a.cursor + 1, (unsigned long long)gathered);
+    return;
+  }
+  if (DUAL) {
+    query_finish<MODE, NT>(a, qbase, cnt, gathered, 0);
+    if (qbase + 1 < a.q_end) {
+      __syncthreads();
+      query_finish<MODE, NT>(a, qbase + 1, cnt, 0, 16);
+    }
+  } else {
+    query_finish<MODE, NT>(a, q, cnt, gathered, 0);
+  }
+}
+
+// threshold + compaction (or the dense row) of a query whose counters were filled by a whole grid
+template <int NT>
+__global__ void __launch_bounds__(NT) query_finish_kernel(QueryArgs a, uint64_t q0) {
+  query_finish<kGlobal32, NT>(a, q0 + blockIdx.x, a.gcounts + (size_t)blockIdx.x * a.n, 0, 0);
 }
 
 }  // namespace nq
@@ -527,66 +661,99 @@ static cudaError_t launch_query_t(size_t smem, unsigned nb, const QueryArgs& a, 
   else k64<<<nb, NT, smem, st>>>(a, q0);
   return cudaSuccess;
 }
-template <typename IT, int MODE, int NT, int SEG, int T>
+template <typename IT, int MODE, int NT, int SEG, int T, bool SPLIT = false>
 static cudaError_t launch_query_seg_t(size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st, int* occ) {
   const bool idx32 = (uint64_t)a.F * a.gid_stride + kQuerySlack < (1ull << 32);
-  constexpr int R = NT == 128 ? 4 : 8;
+  constexpr int R = NT <= 256 ? 4 : 8;
+  constexpr int D = NT <= 256 ? 3 : 2;
+  constexpr unsigned QPC = MODE == kDual16 ? 2 : 1;  // queries per CTA
   // 64-bit posting indexes only occur with global counters (n > 131k at S=15), where shared memory is free
-  auto k32 = query_count_seg_kernel<IT, MODE, NT, uint32_t, SEG, T, R>;
-  auto k64 = query_count_seg_kernel<IT, MODE, NT, uint64_t, SEG, T / 2, R>;  // 16-byte descriptors: half the window
+  auto k32 = query_count_seg_kernel<IT, MODE, NT, uint32_t, SEG, T, R, D, SPLIT>;
+  // 16-byte descriptors: half the window (the split16 form exists with 32-bit posting indexes only)
+  auto k64 = query_count_seg_kernel<IT, MODE, NT, typename std::conditional<SPLIT, uint32_t, uint64_t>::type, SEG, SPLIT ? T : T / 2, R, D, SPLIT>;
   // the segment table is static shared memory on top of the counters: cudaErrorInvalidValue here
   // (counters + table over the per-block limit) sends the caller back to the stream form
   cudaError_t e = cudaFuncSetAttribute(idx32 ? k32 : k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (occ)  // resident CTAs per SM of the kernel that would run (wave sizing), no launch
-    return idx32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k32, NT, smem)
-                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k64, NT, smem);
-  if (idx32) k32<<<nb, NT, smem, st>>>(a, q0);
-  else k64<<<nb, NT, smem, st>>>(a, q0);
+  if (occ) {  // resident QUERIES per SM of the kernel that would run (wave sizing), no launch
+    e = idx32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k32, NT, smem)
+              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k64, NT, smem);
+    *occ *= QPC;
+    return e;
+  }
+  QueryArgs b = a;
+  b.q_end = q0 + nb;
+  const dim3 grid((nb + QPC - 1) / QPC, MODE == kGlobal32 && a.parts ? a.parts : 1);
+  if (MODE == kGlobal32 && a.parts &&
+      (e = cudaMemsetAsync(a.gcounts, 0, (size_t)nb * a.n * sizeof(uint32_t), st)) != cudaSuccess)
+    return e;
+  if (idx32) k32<<<grid, NT, smem, st>>>(b, q0);
+  else k64<<<grid, NT, smem, st>>>(b, q0);
+  if (MODE == kGlobal32 && a.parts) query_finish_kernel<1024><<<nb, 1024, 0, st>>>(b, q0);
   return cudaSuccess;
 }
 // Gather form.  Lists of a shard of n genomes hold ~n * 6.8e-4 postings on bacterial sketches at the
-// default W.  NQ_QUERY_FORM = stream | seg8 | seg16 | seg32 overrides (measurement only).
-enum QueryForm { kFormStream = 0, kFormSeg8 = 8, kFormSeg16 = 16, kFormSeg32 = 32 };
-static int query_form(const QueryArgs& a, bool small) {
+// default W.  NQ_QUERY_FORM = stream | seg8 | seg16 | seg32 | dual8 | dual16 overrides
+// (measurement only).
+enum QueryForm { kFormStream = 0, kFormSeg8 = 8, kFormSeg16 = 16, kFormSeg32 = 32, kFormDual8 = 108, kFormDual16 = 116 };
+// the two-queries-per-CTA counters: S <= 15 (half-word counts), u16 ids that leave room for the
+// dummy ids, and four 256-thread CTAs per SM
+static bool query_dual_ok(const nq_index* ix) {
+  return ix->p.S <= 15 && ix->elem == 2 && (size_t)ix->n * 4 + 128 <= 54 * 1024 && ix->n + 64 < 65536;
+}
+static int query_form(const nq_index* ix, bool small) {
   static const char* env = getenv("NQ_QUERY_FORM");
-  if (env) {
+  const bool seg_ok = (uint64_t)ix->p.F * ix->row_stride < (1ull << 32);  // 32-bit directory indexes
+  if (env && seg_ok) {
     if (!strcmp(env, "stream")) return kFormStream;
     if (!strcmp(env, "seg8")) return kFormSeg8;
     if (!strcmp(env, "seg16")) return kFormSeg16;
     if (!strcmp(env, "seg32")) return kFormSeg32;
+    if (!strcmp(env, "dual8") && query_dual_ok(ix)) return kFormDual8;
+    if (!strcmp(env, "dual16") && query_dual_ok(ix)) return kFormDual16;
   }
-  if (small) return kFormStream;
-  return a.n >= 40000 ? kFormSeg32 : kFormStream;
+  if (!seg_ok) return kFormStream;
+  if (small) return kFormStream;  // dual8/seg8 measured within 2% of it (L2 sector rate bound)
+  return ix->n >= 40000 ? kFormSeg32 : kFormStream;
 }
 template <typename IT>
-static cudaError_t launch_query_it(int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st, int* occ) {
+static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0,
+                                   cudaStream_t st, int* occ) {
   // small counter arrays: 128-thread CTAs (4 warps with ~56 registers each carry a deep gather
   // pipeline, and ~9 queries share an SM); large ones: one big CTA per SM
   const bool small = smem <= 26 * 1024;  // at least 8 such CTAs per SM
-  const int form = query_form(a, small);
+  const int form = query_form(ix, small);
   if (mode == kGlobal32) {
-    if (form == kFormStream) return launch_query_t<IT, kGlobal32, 512>(0, nb, a, q0, st, occ);
+    if (form == kFormStream || !a.parts) return launch_query_t<IT, kGlobal32, 512>(0, nb, a, q0, st, occ);
     return launch_query_seg_t<IT, kGlobal32, 512, 32, 96>(0, nb, a, q0, st, occ);
+  }
+  if (form == kFormDual8 || form == kFormDual16) {
+    const size_t dsmem = (size_t)ix->n * 4 + 128;  // one u32 per genome + the dummy words
+    if (form == kFormDual8) return launch_query_seg_t<IT, kDual16, 256, 8, 64>(dsmem, nb, a, q0, st, occ);
+    return launch_query_seg_t<IT, kDual16, 256, 16, 64>(dsmem, nb, a, q0, st, occ);
   }
 #define NQ_SEG_DISPATCH(MODE)                                                                                      \
   if (small) {                                                                                                     \
-    if (form == kFormSeg8) return launch_query_seg_t<IT, MODE, 128, 8, 64>(smem, nb, a, q0, st, occ);                   \
-    if (form == kFormSeg16) return launch_query_seg_t<IT, MODE, 128, 16, 64>(smem, nb, a, q0, st, occ);                 \
-    if (form == kFormSeg32) return launch_query_seg_t<IT, MODE, 128, 32, 64>(smem, nb, a, q0, st, occ);                 \
-    return launch_query_t<IT, MODE, 128>(smem, nb, a, q0, st, occ);                                                     \
+    if (form == kFormSeg8) return launch_query_seg_t<IT, MODE, 128, 8, 64>(smem, nb, a, q0, st, occ);              \
+    if (form == kFormSeg16) return launch_query_seg_t<IT, MODE, 128, 16, 64>(smem, nb, a, q0, st, occ);            \
+    if (form == kFormSeg32) return launch_query_seg_t<IT, MODE, 128, 32, 64>(smem, nb, a, q0, st, occ);            \
+    return launch_query_t<IT, MODE, 128>(smem, nb, a, q0, st, occ);                                                \
   }                                                                                                                \
-  if (form == kFormSeg8) return launch_query_seg_t<IT, MODE, 1024, 8, 96>(smem, nb, a, q0, st, occ);                    \
-  if (form == kFormSeg16) return launch_query_seg_t<IT, MODE, 1024, 16, 96>(smem, nb, a, q0, st, occ);                  \
-  if (form == kFormSeg32) return launch_query_seg_t<IT, MODE, 1024, 32, 96>(smem, nb, a, q0, st, occ);                  \
+  if (form == kFormSeg8) return launch_query_seg_t<IT, MODE, 1024, 8, 96>(smem, nb, a, q0, st, occ);               \
+  if (form == kFormSeg16) return launch_query_seg_t<IT, MODE, 1024, 16, 96>(smem, nb, a, q0, st, occ);             \
+  if (form == kFormSeg32) return launch_query_seg_t<IT, MODE, 1024, 32, 96>(smem, nb, a, q0, st, occ);             \
   return launch_query_t<IT, MODE, 1024>(smem, nb, a, q0, st, occ);
+  // 65.6k..131k genomes with packed counters: gather from the u16 copy of the postings
+  if (mode == kPack16 && form == kFormSeg32 && a.gids16 && (uint64_t)a.F * a.gid_stride + kQuerySlack < (1ull << 32))
+    return launch_query_seg_t<uint16_t, kPack16, 1024, 32, 96, true>(smem, nb, a, q0, st, occ);
   if (mode == kPack16) { NQ_SEG_DISPATCH(kPack16) }
   NQ_SEG_DISPATCH(kSmem32)
 #undef NQ_SEG_DISPATCH
 }
-static cudaError_t launch_query(uint32_t elem, int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0,
+static cudaError_t launch_query(const nq_index* ix, int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0,
                                 cudaStream_t st, int* occ = nullptr) {
-  return elem == 2 ? launch_query_it<uint16_t>(mode, smem, nb, a, q0, st, occ) : launch_query_it<uint32_t>(mode, smem, nb, a, q0, st, occ);
+  return ix->elem == 2 ? launch_query_it<uint16_t>(ix, mode, smem, nb, a, q0, st, occ)
+                       : launch_query_it<uint32_t>(ix, mode, smem, nb, a, q0, st, occ);
 }
 
 // Queries per launch.  Global counters bound it by memory.  When the L2 prefetch is on (a few
@@ -597,15 +764,26 @@ static cudaError_t launch_query(uint32_t elem, int mode, size_t smem, unsigned n
 // access for two dependent sectors per probe (measured at 12.5k genomes x 10k queries: 13.2 ms
 // as one grid).
 static uint64_t query_wave(const nq_index* ix, int mode, size_t smem, const QueryArgs& a, uint64_t nq) {
-  if (mode == kGlobal32) return std::max<uint64_t>(1, std::min<uint64_t>(nq, (1ull << 30) / ((uint64_t)ix->n * 4)));
+  // global counters: as many queries per launch as keep their counters in L2 (the count kernel's
+  // atomics run ~6x faster there than in HBM: 193 vs 33 G/s measured); the grid is filled by cutting
+  // every query over `parts` CTAs instead (set_query_parts)
+  if (mode == kGlobal32) return std::max<uint64_t>(1, std::min<uint64_t>(nq, (64ull << 20) / ((uint64_t)ix->n * 4)));
   static const char* env = getenv("NQ_QUERY_WAVES");  // "0": one grid (measurement only)
   if (!a.prefetch || (env && env[0] == '0')) return nq;
   int occ = 0;
-  if (launch_query(ix->elem, mode, smem, 1, a, 0, nullptr, &occ) != cudaSuccess || occ <= 0) return nq;
+  if (launch_query(ix, mode, smem, 1, a, 0, nullptr, &occ) != cudaSuccess || occ <= 0) return nq;
   const uint64_t slots = (uint64_t)occ * ix->ctx->sm_count;
   if (nq <= slots) return nq;
   const uint64_t waves = (nq + slots - 1) / slots;
   return (nq + waves - 1) / waves;
+}
+
+// CTAs per query of the global-counter form: two resident waves of 512-thread CTAs over the launch
+static void set_query_parts(const nq_index* ix, int mode, uint64_t q_per_launch, QueryArgs& a) {
+  a.parts = 0;
+  if (mode != kGlobal32 || query_form(ix, false) == kFormStream) return;
+  const uint64_t ctas = (uint64_t)ix->ctx->sm_count * 4 * 2;
+  a.parts = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(2048, ctas / std::max<uint64_t>(1, q_per_launch)));
 }
 
 // counter mode and dynamic shared memory of the query kernel for this index
@@ -624,16 +802,24 @@ int nq_query_prepare(nq_index* ix) {
   size_t smem;
   query_layout(ix, mode, smem);
   const uint32_t words = mode == kPack16 ? (ix->n + 1) / 2 : ix->n;
-  uint16_t h16[32];
-  uint32_t h32[32];
+  uint16_t h16[64];
+  uint32_t h32[64];
   for (uint32_t l = 0; l < 32; ++l) {
     h32[l] = query_dummy_id<uint32_t>(mode, words, l);
     h16[l] = (uint16_t)query_dummy_id<uint16_t>(mode, words, l);
     if (ix->elem == 2 && mode != kGlobal32 && h32[l] > 0xFFFFu) return nq_set_error(NQ_ERR_INVALID, "dummy id overflow");
+    // second set (slack elements 32..63): the two-queries-per-CTA form counts into word `id`
+    h32[32 + l] = query_dummy_id<uint32_t>(kDual16, ix->n, l);
+    h16[32 + l] = (uint16_t)h32[32 + l];  // only used when query_dual_ok() (n + 64 < 65536)
   }
   char* end = static_cast<char*>(ix->d_gids) + (size_t)ix->p.F * ix->gid_stride * ix->elem;
-  NQ_CUDA(cudaMemcpyAsync(end, ix->elem == 2 ? (const void*)h16 : (const void*)h32, 32 * ix->elem, cudaMemcpyHostToDevice,
+  NQ_CUDA(cudaMemcpyAsync(end, ix->elem == 2 ? (const void*)h16 : (const void*)h32, 64 * ix->elem, cudaMemcpyHostToDevice,
                           ix->ctx->stream));
+  if (ix->d_gids16) {  // split16 copy: dead lanes count as "high", so their dummy id is stored minus 2^16
+    for (uint32_t l = 0; l < 32; ++l) h16[l] = (uint16_t)(h32[l] - 65536u);
+    NQ_CUDA(cudaMemcpyAsync(ix->d_gids16 + (size_t)ix->p.F * ix->gid_stride, h16, 32 * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                            ix->ctx->stream));
+  }
   NQ_CUDA(cudaStreamSynchronize(ix->ctx->stream));  // the staging arrays live on this stack frame
   return NQ_OK;
 }
@@ -653,6 +839,7 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
   a.qsk = d_sketches; a.dir = ix->d_row; a.gids = ix->d_gids;
   a.F = p.F; a.range = (uint32_t)p.range; a.n = ix->n; a.row_stride = ix->row_stride; a.gid_stride = ix->gid_stride;
   a.gid_base = ix->gid_base;
+  a.dir3 = ix->d_dir3; a.gids16 = ix->d_gids16;
   a.min_score = min_score;
   a.wrap_mask = p.S <= 7 ? 0xFFu : p.S <= 15 ? 0xFFFFu : 0xFFFFFFFFu;  // counter widths of :635/:651/:667
 
@@ -663,6 +850,7 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
   a.prefetch = (uint64_t)(kPfAhead + 1) * kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem <= (64ull << 20);
 
   const uint64_t q_per_launch = query_wave(ix, mode, smem, a, nq);
+  set_query_parts(ix, mode, q_per_launch, a);
 
   unsigned long long* d_cursor = nullptr;
   uint64_t* d_begin = nullptr;
@@ -701,7 +889,7 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
     NqTimer* timer = new NqTimer(ctx, NQK_QUERY);
     for (uint64_t q0 = 0; q0 < nq; q0 += q_per_launch) {
       const unsigned nb = (unsigned)std::min<uint64_t>(q_per_launch, nq - q0);
-      const cudaError_t e0 = launch_query(ix->elem, mode, smem, nb, a, q0, ctx->stream);
+      const cudaError_t e0 = launch_query(ix, mode, smem, nb, a, q0, ctx->stream);
       cudaError_t e = e0;
       ctx->launches++;
       if (e != cudaSuccess || (e = cudaPeekAtLastError()) != cudaSuccess) {
@@ -762,6 +950,7 @@ int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, ui
   a.qsk = d_sketches; a.dir = ix->d_row; a.gids = ix->d_gids;
   a.F = p.F; a.range = (uint32_t)p.range; a.n = ix->n; a.row_stride = ix->row_stride; a.gid_stride = ix->gid_stride;
   a.gid_base = ix->gid_base;
+  a.dir3 = ix->d_dir3; a.gids16 = ix->d_gids16;
   a.wrap_mask = wrap_mask;
   a.dense = d_out;
   int mode;
@@ -769,6 +958,7 @@ int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, ui
   query_layout(ix, mode, smem);
   a.prefetch = (uint64_t)(kPfAhead + 1) * kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem <= (64ull << 20);
   const uint64_t q_per_launch = query_wave(ix, mode, smem, a, nq);
+  set_query_parts(ix, mode, q_per_launch, a);
   unsigned long long* d_cursor = nullptr;  // [1] = gather statistics
   NQ_TRY(nq_dmalloc(ctx, (void**)&d_cursor, 16));
   if (mode == kGlobal32) {
@@ -781,7 +971,7 @@ int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, ui
     NqTimer timer(ctx, NQK_MATRIX);
     for (uint64_t q0 = 0; q0 < nq && e == cudaSuccess; q0 += q_per_launch) {
       const unsigned nb = (unsigned)std::min<uint64_t>(q_per_launch, nq - q0);
-      e = launch_query(ix->elem, mode, smem, nb, a, q0, ctx->stream);
+      e = launch_query(ix, mode, smem, nb, a, q0, ctx->stream);
       ctx->launches++;
       if (e == cudaSuccess) e = cudaPeekAtLastError();
     }
