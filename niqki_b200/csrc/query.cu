@@ -41,6 +41,9 @@ struct QueryArgs {
   uint64_t* hit_begin;  // [nq]
   uint32_t* hit_n;      // [nq]
   uint32_t* gcounts;    // global counters [gridDim.x][n] (GLOBAL mode only)
+  uint32_t* slice_hits;           // GLOBAL mode finish scratch: [queries per launch][slices]
+  unsigned long long* slice_base;
+  uint32_t slices;
   uint32_t parts;       // GLOBAL mode, segment-table form: gridDim.y CTAs share one query (counters zeroed before, finished after)
   uint32_t prefetch;    // cooperative L2 prefetch of upcoming cells (only when a few chunks of cells fit in L2)
   const uint4* dir3;       // split16 side arrays of the index (internal.h), or null
@@ -419,7 +422,7 @@ struct SegRef {
 // `gids16` and the directory from `dir3` {begin, mid, end}: ids from position `mid` of a list on
 // are >= 65536 and get the 2^16 back when they are counted.  Which lanes of a round lie past `mid`
 // is known at gather time only, so one bit per round is kept beside each ring slot (`hmask`).  A
-// segment descriptor carries {postings left, min(postings left, ids below 2^16 left)} as two
+// segment descriptor carries {postings left (high), min(postings left, ids below 2^16 left) (low)} as two
 // half-words: lanes at or past the second number are "high", which includes the dead lanes of a
 // list's last round — their dummy id is stored minus 2^16.
 template <typename IT, int MODE, int NT, typename IDX, int SEG, int T, int R, int D, bool SPLIT = false>
@@ -498,22 +501,39 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : 1) query_c
 #pragma unroll
   for (int d = 0; d < D; ++d) live[d] = hmask[d] = 0;
   uint32_t phase = 0;
+  // split16 count of round k: id = l + 2^16 * bit k of hm; word (id >> 1), increment 1 or 2^16.  Written as
+  // AND + multiply-add pairs so that half of it runs on the (idle) FMA pipe: byte address =
+  // (l & ~1) * 2 + (hm & 2^k) * 2^(17-k), increment = (l & 1) * 0xFFFF + 1.
+  auto count_split = [&](uint32_t l, uint32_t hm, int k) {
+    uint32_t off, addr, inc;
+    asm("mad.lo.u32 %0, %1, %2, 0;" : "=r"(off) : "r"(hm & (1u << k)), "r"(1u << (17 - k)));
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(l & ~1u), "r"(off));
+    asm("mad.lo.u32 %0, %1, 0xFFFF, 1;" : "=r"(inc) : "r"(l & 1u));
+    atomicAdd(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem) + addr), inc);
+  };
   auto drain = [&](uint32_t (&l)[R], uint32_t hm, uint32_t nl) {
     if (nl >= (uint32_t)R) {
 #pragma unroll
-      for (int k = 0; k < R; ++k) count(SPLIT ? l[k] + (((hm >> k) & 1u) << 16) : l[k]);
+      for (int k = 0; k < R; ++k) {
+        if (SPLIT) count_split(l[k], hm, k);
+        else count(l[k]);
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < R - 1; ++k)
-        if ((uint32_t)k < nl) count(SPLIT ? l[k] + (((hm >> k) & 1u) << 16) : l[k]);
+        if ((uint32_t)k < nl) {
+          if (SPLIT) count_split(l[k], hm, k);
+          else count(l[k]);
+        }
     }
   };
+  const uint32_t sub_hi = (sub << 16) | 0xFFFFu;
   auto gather_round = [&](uint32_t& dst, uint32_t& hm, const SegRef<IDX>* t, int k) {
     const SegRef<IDX> d = t[k * SPR + grp];
     if (SPLIT) {
-      const uint32_t rem = (uint32_t)d.rem & 0xFFFFu, below = (uint32_t)d.rem >> 16;
-      dst = gids[sub < rem ? d.at + sub : dead_at];
-      hm |= (sub >= below ? 1u : 0u) << k;
+      // d.rem = postings left << 16 | ids below 2^16 left (<= postings left):  sub < left  <=>  sub_hi < d.rem
+      dst = gids[sub_hi < (uint32_t)d.rem ? d.at + sub : dead_at];
+      hm |= (sub >= ((uint32_t)d.rem & 0xFFFFu) ? 1u : 0u) << k;
     } else {
       dst = gids[(int32_t)sub < d.rem ? d.at + sub : dead_at];
     }
@@ -561,7 +581,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : 1) query_c
         return SegRef<IDX>{at, (int32_t)(len - k)};
       } else {
         const uint32_t rem = min(len - k, 0xFFFFu), below = low > k ? min(low - k, rem) : 0u;
-        return SegRef<IDX>{at, (int32_t)(rem | (below << 16))};
+        return SegRef<IDX>{at, (int32_t)((rem << 16) | below)};
       }
     };
     const uint32_t nseg = (len + SEG - 1) / SEG;
@@ -635,10 +655,87 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : 1) query_c
   }
 }
 
-// threshold + compaction (or the dense row) of a query whose counters were filled by a whole grid
+// ---- threshold + compaction (or the dense row) of queries whose counters were filled by a whole
+// grid.  n is in the millions here, so the genomes of a query are cut into gridDim.y slices:
+//   global_hits_count_kernel   hits per (query, slice)
+//   global_hits_reserve_kernel per query: exclusive offsets of its slices + one pool reservation
+//   global_hits_write_kernel   (count, gid) in gid order inside each slice, slices in order
+// (or global_dense_kernel alone when the whole counter row is wanted).
+__device__ __forceinline__ void slice_of(const QueryArgs& a, uint32_t& g_lo, uint32_t& g_hi) {
+  const uint32_t per = (a.n + gridDim.y - 1) / gridDim.y;
+  g_lo = min(a.n, blockIdx.y * per);
+  g_hi = min(a.n, g_lo + per);
+}
 template <int NT>
-__global__ void __launch_bounds__(NT) query_finish_kernel(QueryArgs a, uint64_t q0) {
-  query_finish<kGlobal32, NT>(a, q0 + blockIdx.x, a.gcounts + (size_t)blockIdx.x * a.n, 0, 0);
+__global__ void __launch_bounds__(NT) global_hits_count_kernel(QueryArgs a, uint32_t* __restrict__ slice_hits) {
+  __shared__ uint32_t s_warp[NT / 32];
+  const uint32_t* cnt = a.gcounts + (size_t)blockIdx.x * a.n;
+  uint32_t g_lo, g_hi;
+  slice_of(a, g_lo, g_hi);
+  uint32_t mine = 0;
+  for (uint32_t g = g_lo + threadIdx.x; g < g_hi; g += NT) mine += (__ldcg(&cnt[g]) & a.wrap_mask) >= a.min_score;
+  mine = __reduce_add_sync(0xFFFFFFFFu, mine);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < NT / 32; ++w) t += s_warp[w];
+    slice_hits[(size_t)blockIdx.x * gridDim.y + blockIdx.y] = t;
+  }
+}
+__global__ void global_hits_reserve_kernel(QueryArgs a, uint64_t q0, uint32_t nb, uint32_t slices, uint32_t* __restrict__ slice_hits,
+                                           unsigned long long* __restrict__ slice_base) {
+  const uint32_t ql = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ql >= nb) return;
+  uint32_t total = 0;
+  for (uint32_t s = 0; s < slices; ++s) total += slice_hits[(size_t)ql * slices + s];
+  unsigned long long base = atomicAdd(a.cursor, (unsigned long long)total);
+  a.hit_begin[q0 + ql] = base;
+  a.hit_n[q0 + ql] = total;
+  const bool fits = base + total <= a.pool_cap;  // overflow: nothing is written, the host re-runs with a larger pool
+  for (uint32_t s = 0; s < slices; ++s) {
+    slice_base[(size_t)ql * slices + s] = fits ? base : ~0ull;
+    base += slice_hits[(size_t)ql * slices + s];
+  }
+}
+template <int NT>
+__global__ void __launch_bounds__(NT) global_hits_write_kernel(QueryArgs a, const uint32_t* __restrict__ slice_hits,
+                                                               const unsigned long long* __restrict__ slice_base) {
+  __shared__ uint32_t s_warp[NT / 32];
+  const size_t sl = (size_t)blockIdx.x * gridDim.y + blockIdx.y;
+  const unsigned long long base = slice_base[sl];
+  if (slice_hits[sl] == 0 || base == ~0ull) return;
+  const uint32_t* cnt = a.gcounts + (size_t)blockIdx.x * a.n;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t g_lo, g_hi;
+  slice_of(a, g_lo, g_hi);
+  uint32_t done = 0;
+  for (uint32_t g0 = g_lo; g0 < g_hi; g0 += NT) {
+    const uint32_t g = g0 + tid;
+    const uint32_t c = g < g_hi ? __ldcg(&cnt[g]) & a.wrap_mask : 0u;
+    const bool hit = g < g_hi && c >= a.min_score;
+    if (__syncthreads_count(hit) == 0) continue;
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, chunk = 0;
+    for (int w = 0; w < NT / 32; ++w) {
+      const uint32_t x = s_warp[w];
+      before += w < (int)warp ? x : 0;
+      chunk += x;
+    }
+    if (hit) a.pool[base + done + before + __popc(bal & ((1u << lane) - 1))] = ((uint64_t)c << 32) | (a.gid_base + g);
+    done += chunk;
+    __syncthreads();
+  }
+}
+template <int NT>
+__global__ void __launch_bounds__(NT) global_dense_kernel(QueryArgs a, uint64_t q0) {
+  const uint32_t* cnt = a.gcounts + (size_t)blockIdx.x * a.n;
+  uint32_t* row = a.dense + (q0 + blockIdx.x) * a.n;
+  uint32_t g_lo, g_hi;
+  slice_of(a, g_lo, g_hi);
+  for (uint32_t g = g_lo + threadIdx.x; g < g_hi; g += NT) row[g] = __ldcg(&cnt[g]) & a.wrap_mask;
 }
 
 }  // namespace nq
@@ -689,7 +786,16 @@ static cudaError_t launch_query_seg_t(size_t smem, unsigned nb, const QueryArgs&
     return e;
   if (idx32) k32<<<grid, NT, smem, st>>>(b, q0);
   else k64<<<grid, NT, smem, st>>>(b, q0);
-  if (MODE == kGlobal32 && a.parts) query_finish_kernel<1024><<<nb, 1024, 0, st>>>(b, q0);
+  if (MODE == kGlobal32 && a.parts) {
+    const dim3 fg(nb, a.slices);
+    if (a.dense) {
+      global_dense_kernel<1024><<<fg, 1024, 0, st>>>(b, q0);
+    } else {
+      global_hits_count_kernel<1024><<<fg, 1024, 0, st>>>(b, a.slice_hits);
+      global_hits_reserve_kernel<<<(nb + 127) / 128, 128, 0, st>>>(b, q0, nb, a.slices, a.slice_hits, a.slice_base);
+      global_hits_write_kernel<1024><<<fg, 1024, 0, st>>>(b, a.slice_hits, a.slice_base);
+    }
+  }
   return cudaSuccess;
 }
 // Gather form.  Lists of a shard of n genomes hold ~n * 6.8e-4 postings on bacterial sketches at the
@@ -721,7 +827,7 @@ static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, un
                                    cudaStream_t st, int* occ) {
   // small counter arrays: 128-thread CTAs (4 warps with ~56 registers each carry a deep gather
   // pipeline, and ~9 queries share an SM); large ones: one big CTA per SM
-  const bool small = smem <= 26 * 1024;  // at least 8 such CTAs per SM
+  const bool small = mode != kGlobal32 && smem <= 26 * 1024;  // at least 8 such CTAs per SM
   const int form = query_form(ix, small);
   if (mode == kGlobal32) {
     if (form == kFormStream || !a.parts) return launch_query_t<IT, kGlobal32, 512>(0, nb, a, q0, st, occ);
@@ -779,11 +885,15 @@ static uint64_t query_wave(const nq_index* ix, int mode, size_t smem, const Quer
 }
 
 // CTAs per query of the global-counter form: two resident waves of 512-thread CTAs over the launch
-static void set_query_parts(const nq_index* ix, int mode, uint64_t q_per_launch, QueryArgs& a) {
+static int set_query_parts(const nq_index* ix, int mode, uint64_t q_per_launch, QueryArgs& a) {
   a.parts = 0;
-  if (mode != kGlobal32 || query_form(ix, false) == kFormStream) return;
+  if (mode != kGlobal32 || query_form(ix, false) == kFormStream) return NQ_OK;
   const uint64_t ctas = (uint64_t)ix->ctx->sm_count * 4 * 2;
   a.parts = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(2048, ctas / std::max<uint64_t>(1, q_per_launch)));
+  a.slices = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(1024, ((uint64_t)ix->n + 65535) / 65536));
+  NQ_TRY(nq_dmalloc(ix->ctx, (void**)&a.slice_hits, q_per_launch * a.slices * sizeof(uint32_t)));
+  NQ_TRY(nq_dmalloc(ix->ctx, (void**)&a.slice_base, q_per_launch * a.slices * sizeof(unsigned long long)));
+  return NQ_OK;
 }
 
 // counter mode and dynamic shared memory of the query kernel for this index
@@ -850,7 +960,7 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
   a.prefetch = (uint64_t)(kPfAhead + 1) * kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem <= (64ull << 20);
 
   const uint64_t q_per_launch = query_wave(ix, mode, smem, a, nq);
-  set_query_parts(ix, mode, q_per_launch, a);
+  if (set_query_parts(ix, mode, q_per_launch, a) != NQ_OK) { nq_dfree(ctx, a.slice_hits); delete hits; return NQ_ERR_CUDA; }
 
   unsigned long long* d_cursor = nullptr;
   uint64_t* d_begin = nullptr;
@@ -859,6 +969,7 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
   int st = NQ_OK;
   auto cleanup = [&]() {
     nq_dfree(ctx, d_cursor); nq_dfree(ctx, d_begin); nq_dfree(ctx, d_n); nq_dfree(ctx, d_gcounts);
+    nq_dfree(ctx, a.slice_hits); nq_dfree(ctx, a.slice_base);
   };
   auto fail = [&](int s) {
     cleanup();
@@ -958,7 +1069,7 @@ int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, ui
   query_layout(ix, mode, smem);
   a.prefetch = (uint64_t)(kPfAhead + 1) * kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem <= (64ull << 20);
   const uint64_t q_per_launch = query_wave(ix, mode, smem, a, nq);
-  set_query_parts(ix, mode, q_per_launch, a);
+  if (set_query_parts(ix, mode, q_per_launch, a) != NQ_OK) { nq_dfree(ctx, a.slice_hits); return NQ_ERR_CUDA; }
   unsigned long long* d_cursor = nullptr;  // [1] = gather statistics
   NQ_TRY(nq_dmalloc(ctx, (void**)&d_cursor, 16));
   if (mode == kGlobal32) {
@@ -978,6 +1089,8 @@ int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, ui
   }
   nq_dfree(ctx, d_cursor);
   nq_dfree(ctx, a.gcounts);
+  nq_dfree(ctx, a.slice_hits);
+  nq_dfree(ctx, a.slice_base);
   if (e != cudaSuccess) return nq_set_error(NQ_ERR_CUDA, "matrix row kernel launch failed: %s", cudaGetErrorString(e));
   return NQ_OK;
 }

@@ -296,6 +296,108 @@ __global__ void __launch_bounds__(NT) densify_kernel(uint32_t* gsk, DevParams P,
   if (empty != 0 && flags && threadIdx.x == 0) flags[blockIdx.x] |= NQ_ENTRY_DENSIFY_STALLED;
 }
 
+// ------------------------------------------------------------------------------------------
+// Short entries (--indexlines / --querylines: one read per entry, small S): one WARP per entry,
+// sketch + densification fused, everything in the warp's slice of shared memory.  The CTA-per-entry
+// kernels above leave 126 of 128 threads idle on a 150 bp read and pay two launches' worth of
+// global sketch traffic; here lane l rolls its own run of ~nk/32 k-mers from scratch — the K-1
+// characters before a run are re-read by the lane, with the record-seed rule (str2numstrand,
+// :255-273: both cases accepted, one foreign byte zeroes the whole seed, B4) applied by POSITION
+// (characters 0..K-2 of the entry) so that a run may start anywhere — and densification (:313-331,
+// same lowest-index-source rule as densify_kernel) runs on the warp with the two hash_family
+// terms of every cell cached beside it (they are functions of the cell's value, copied along).
+// ------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) sketch_reads_kernel(const uint8_t* __restrict__ bases,
+                                                               const uint64_t* __restrict__ offsets, uint64_t n,
+                                                               uint32_t* __restrict__ gsk, DevParams P,
+                                                               uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) uint32_t smem[];  // per warp: sk[F] | ab[F] ({family_a, family_b} as two u16)
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t F = P.F, Fmask = F - 1, K = P.K;
+  uint32_t* sk = smem + (size_t)warp * 2 * F;
+  uint32_t* ab = sk + F;
+  constexpr unsigned kFull = 0xFFFFFFFFu;
+  for (uint64_t entry = (uint64_t)blockIdx.x * NW + warp; entry < n; entry += (uint64_t)gridDim.x * NW) {
+    const uint64_t E0 = offsets[entry], L = offsets[entry + 1] - E0;
+    uint32_t* grow = gsk + entry * F;
+    for (uint32_t i = lane; i < F; i += 32) sk[i] = kEmpty;
+    __syncwarp();
+    if (L > K) {
+      const uint32_t nk = (uint32_t)(L - K);  // k-mers 0..L-K-1: the last one is skipped (:342, B2)
+      const uint8_t* e = bases + E0;
+      // seed rule: any foreign byte among the first K-1 characters zeroes all of them
+      const bool seed_ok = __all_sync(kFull, lane + 1 >= K || seed_code(e[lane]) < 4);
+      const uint32_t run = (nk + 31) / 32, lo = lane * run, hi = min(nk, lo + run);
+      if (lo < hi) {
+        uint64_t f = 0, r = 0;
+        auto roll_at = [&](uint32_t x) {
+          const uint32_t c = e[x];
+          uint32_t fw, rv;
+          if (x + 1 < K) { fw = seed_ok ? seed_code(c) : 0u; rv = 3u - fw; }  // seed region (:255-273, :240-250)
+          else { fw = fw_code(c); rv = rv_code(c); }                          // rolled characters (:114-123, :211-221)
+          f = ((f << 2) + fw) & P.kmask;                 // :225-229
+          r = (r >> 2) + ((uint64_t)rv << P.rc_shift);   // :233-236
+        };
+        for (uint32_t j = 0; j + 1 < K; ++j) roll_at(lo + j);
+        for (uint32_t p = lo; p < hi; ++p) {
+          roll_at(p + K - 1);
+          const uint64_t canon = f < r ? f : r;                                            // :345
+          const uint32_t b = (uint32_t)(unrevhash64(canon) >> (64 - P.S));                 // :347
+          atomicMin(&sk[b], fingerprint(revhash64(canon), P.mask_M, P.maxrem, P.M));       // :346, :348-355
+        }
+      }
+    }
+    __syncwarp();
+    // ---- densification
+    uint32_t my_empty = 0;
+    for (uint32_t i = lane; i < F; i += 32) {
+      const uint32_t v = sk[i];
+      if (v == kEmpty) ++my_empty;
+      else ab[i] = family_a(v, Fmask) | (family_b(v, Fmask) << 16);
+    }
+    uint32_t empty = __reduce_add_sync(kFull, my_empty);
+    uint32_t fl = 0;
+    if (empty == F) {
+      fl = NQ_ENTRY_SKIPPED;  // nothing was sketched (len <= K)
+    } else if (empty) {
+      __syncwarp();
+      uint32_t step = 0, idle = 0;
+      while (empty != 0 && idle < F) {
+        for (uint32_t i = lane; i < F; i += 32) {
+          const uint32_t v = sk[i];
+          if (v < kTent) {
+            const uint32_t h = ab[i];
+            const uint32_t t = ((h & 0xFFFFu) + step * (h >> 16)) & Fmask;
+            if (sk[t] >= kTent) atomicMin(&sk[t], kTent | i);
+          }
+        }
+        __syncwarp();
+        uint32_t filled = 0;
+        for (uint32_t i = lane; i < F; i += 32) {
+          const uint32_t x = sk[i];
+          if (x >= kTent && x != kEmpty) {
+            const uint32_t src = x & ~kTent;
+            sk[i] = sk[src];
+            ab[i] = ab[src];
+            ++filled;
+          }
+        }
+        const uint32_t got = __reduce_add_sync(kFull, filled);
+        __syncwarp();
+        empty -= got;
+        idle = got ? 0 : idle + 1;
+        ++step;
+      }
+      if (empty) fl = NQ_ENTRY_DENSIFY_STALLED;
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < F; i += 32) grow[i] = sk[i];
+    if (flags && lane == 0) flags[entry] = fl;
+    __syncwarp();
+  }
+}
+
 static DevParams make_dev_params(const nq_params* p) {
   DevParams d;
   d.K = p->K; d.S = p->S; d.W = p->W; d.M = p->M; d.F = p->F;
@@ -363,6 +465,31 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
     if (len > p->K) {
       total_k += len - p->K;
       longest = std::max(longest, len - p->K);
+    }
+  }
+  // short entries, small sketches (lines mode): warp-per-entry fused kernel, no global sketch traffic
+  if (!h_rec_entry && longest + p->K <= 4096 && P.S <= 11 && P.K <= 32) {
+    static const char* env = getenv("NQ_READS_KERNEL");  // "0": the CTA-per-entry kernels (measurement only)
+    if (!(env && env[0] == '0')) {
+      constexpr int NW = 8;
+      const size_t smem = (size_t)NW * 2 * P.F * 4;
+      uint64_t* d_offsets = nullptr;
+      NQ_TRY(nq_dmalloc(ctx, (void**)&d_offsets, (n + 1) * sizeof(uint64_t)));
+      NQ_CUDA(cudaMemcpyAsync(d_offsets, h_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+      NQ_CUDA(cudaFuncSetAttribute(sketch_reads_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 1;
+      NQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_reads_kernel<NW>, NW * 32, smem));
+      const unsigned grid = (unsigned)std::min<uint64_t>((n + NW - 1) / NW, (uint64_t)ctx->sm_count * std::max(per_sm, 1));
+      {
+        NqTimer timer(ctx, NQK_SCAN);
+        sketch_reads_kernel<NW><<<grid, NW * 32, smem, ctx->stream>>>(reinterpret_cast<const uint8_t*>(d_bases), d_offsets, n,
+                                                                       reinterpret_cast<uint32_t*>(d_sketches), P, d_flags);
+      }
+      ctx->launches++;
+      const cudaError_t le = cudaPeekAtLastError();
+      nq_dfree(ctx, d_offsets);
+      if (le != cudaSuccess) return nq_set_error(NQ_ERR_CUDA, "sketch_reads_kernel launch failed: %s", cudaGetErrorString(le));
+      return NQ_OK;
     }
   }
   if (total_k == 0) return nq_launch_densify(ctx, p, d_sketches, n_entries, d_flags);

@@ -450,6 +450,44 @@ def test_reads_lines_mode_small(nb, ctx):
     assert np.array_equal(ptr, ohp) and np.array_equal(c, oc) and np.array_equal(gid, og)
 
 
+@pytest.mark.parametrize("ps", [dict(K=31, S=8, W=12, H=4), dict(K=21, S=4, W=10, H=3), dict(K=27, S=10, W=12, H=4),
+                                dict(K=15, S=11, W=8, H=2)])
+def test_reads_kernel_edge_cases(nb, ctx, ps):
+    """Warp-per-entry fused sketch + densification (short entries, S <= 11): ragged lengths around K,
+    empty entries, lower case / N / foreign bytes inside and outside the K-1 seed characters (B3, B4),
+    entries whose densification never ends (flagged, scan part still exact)."""
+    rng = np.random.default_rng(ps["K"] * 100 + ps["S"])
+    o = oracle(**ps)
+    g = gpu_index(nb, ctx, **ps)
+    K = ps["K"]
+    dna = lambda n: random_dna(rng, n).tobytes()  # noqa: E731
+    seqs = [b"", b"A", dna(K - 1), dna(K), dna(K + 1), dna(K + 2)]
+    for L in (40, 64, 65, 100, 150, 151, 250, 1000, 4000):
+        for variant in range(4):
+            s = bytearray(dna(L))
+            if variant == 1:   # lower case in the seed and beyond
+                for pos in rng.integers(0, L, size=max(1, L // 10)):
+                    s[pos] = ord(chr(s[pos]).lower())
+            elif variant == 2:  # a foreign byte inside the seed
+                s[int(rng.integers(0, K - 1))] = ord("N")
+            elif variant == 3:  # foreign bytes after the seed
+                for pos in rng.integers(K - 1, L, size=max(1, L // 20)):
+                    s[pos] = ord("N") if pos % 2 else ord("x")
+            seqs.append(bytes(s))
+    sks, flags = g.sketch_many(seqs)
+    flags = np.asarray(flags)
+    for i, sq in enumerate(seqs):
+        exp, passes = o.compute_sketch(sq, max_passes=20000)
+        scan, filled = o.sketch_scan(sq)
+        if len(sq) <= K:
+            assert flags[i] & 1 and (sks[i] == -1).all(), i
+        elif passes < 0:  # the reference would spin forever
+            assert flags[i] & 2, i
+            assert np.array_equal(sks[i][scan != -1], scan[scan != -1]), i
+        else:
+            assert flags[i] == 0 and np.array_equal(sks[i], exp), (i, len(sq))
+
+
 def test_full_size_properties(nb, ctx):
     """BASELINE-sized entries (5 Mbp, defaults), checked through size-independent properties:
     sketching is deterministic, a genome's best hit is itself with count F, mutated copies rank

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q --timeout 900 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $? : $(tail -1 gpurun_out/pytest_gpu.log)"
-timeout 900 python bench.py --workload c4 --steps 2 --warmup 1 > gpurun_out/c4.json 2> gpurun_out/c4.err
+timeout 900 python bench.py --workload c4 --steps 2 --warmup 1 --queries ${C4Q:-2000} > gpurun_out/c4.json 2> gpurun_out/c4.err
 echo "c4 exit $?"; python - <<'PY'
 import json
 j=json.loads(open("gpurun_out/c4.json").read().strip().splitlines()[-1])
