@@ -804,9 +804,11 @@ def main():
                                  "frac": scan_gbases / hbm_peak if scan_gbases else None,
                                  "note": "1 B/base algorithmic: this kernel is not HBM-bound"}},
             # the HBM-bound kernel of the path (north_star target >= 0.5)
-            "roofline_query": {"kernel": "query_count_kernel", "bound": "hbm", "achieved": q_gbs, "peak": hbm_peak,
+            "roofline_query": {"kernel": "query_count_seg_kernel (seg8 form)" if os.environ.get("NQ_QUERY_FORM", "seg8") == "seg8"
+                               else "query_count_kernel", "bound": "hbm", "achieved": q_gbs, "peak": hbm_peak,
                                "unit": "GB/s", "frac": (q_gbs / hbm_peak) if q_gbs else None,
-                               "traffic": ncu_traffic("query_count_kernel"), "peak_source": peak_src,
+                               "traffic": ncu_traffic("query_count_seg_kernel" if os.environ.get("NQ_QUERY_FORM", "seg8") == "seg8"
+                                                      else "query_count_kernel"), "peak_source": peak_src,
                                "algorithmic_bytes": q_bytes, "gathered_postings": gathered,
                                "launches": int(q_n), "ms_per_launch": q_ms / max(q_n, 1)},
             "roofline_build": {"kernel": "cell_build_kernel", "bound": "hbm", "achieved": b_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -422,7 +422,7 @@ struct SegRef {
 // `gids16` and the directory from `dir3` {begin, mid, end}: ids from position `mid` of a list on
 // are >= 65536 and get the 2^16 back when they are counted.  Which lanes of a round lie past `mid`
 // is known at gather time only, so one bit per round is kept beside each ring slot (`hmask`).  A
-// segment descriptor carries {postings left (high), min(postings left, ids below 2^16 left) (low)} as two
+// segment descriptor carries {postings left, min(postings left, ids below 2^16 left)} as two
 // half-words: lanes at or past the second number are "high", which includes the dead lanes of a
 // list's last round — their dummy id is stored minus 2^16.
 template <typename IT, int MODE, int NT, typename IDX, int SEG, int T, int R, int D, bool SPLIT = false>
@@ -501,39 +501,24 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : 1) query_c
 #pragma unroll
   for (int d = 0; d < D; ++d) live[d] = hmask[d] = 0;
   uint32_t phase = 0;
-  // split16 count of round k: id = l + 2^16 * bit k of hm; word (id >> 1), increment 1 or 2^16.  Written as
-  // AND + multiply-add pairs so that half of it runs on the (idle) FMA pipe: byte address =
-  // (l & ~1) * 2 + (hm & 2^k) * 2^(17-k), increment = (l & 1) * 0xFFFF + 1.
-  auto count_split = [&](uint32_t l, uint32_t hm, int k) {
-    uint32_t off, addr, inc;
-    asm("mad.lo.u32 %0, %1, %2, 0;" : "=r"(off) : "r"(hm & (1u << k)), "r"(1u << (17 - k)));
-    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(l & ~1u), "r"(off));
-    asm("mad.lo.u32 %0, %1, 0xFFFF, 1;" : "=r"(inc) : "r"(l & 1u));
-    atomicAdd(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem) + addr), inc);
-  };
+  // (split16: AND + multiply-add forms of this count on the FMA pipe, and a validity test on the
+  // packed descriptor word, measured 6 % slower than the plain form — 34.6 vs 32.6 ms)
   auto drain = [&](uint32_t (&l)[R], uint32_t hm, uint32_t nl) {
     if (nl >= (uint32_t)R) {
 #pragma unroll
-      for (int k = 0; k < R; ++k) {
-        if (SPLIT) count_split(l[k], hm, k);
-        else count(l[k]);
-      }
+      for (int k = 0; k < R; ++k) count(SPLIT ? l[k] + (((hm >> k) & 1u) << 16) : l[k]);
     } else {
 #pragma unroll
       for (int k = 0; k < R - 1; ++k)
-        if ((uint32_t)k < nl) {
-          if (SPLIT) count_split(l[k], hm, k);
-          else count(l[k]);
-        }
+        if ((uint32_t)k < nl) count(SPLIT ? l[k] + (((hm >> k) & 1u) << 16) : l[k]);
     }
   };
-  const uint32_t sub_hi = (sub << 16) | 0xFFFFu;
   auto gather_round = [&](uint32_t& dst, uint32_t& hm, const SegRef<IDX>* t, int k) {
     const SegRef<IDX> d = t[k * SPR + grp];
     if (SPLIT) {
-      // d.rem = postings left << 16 | ids below 2^16 left (<= postings left):  sub < left  <=>  sub_hi < d.rem
-      dst = gids[sub_hi < (uint32_t)d.rem ? d.at + sub : dead_at];
-      hm |= (sub >= ((uint32_t)d.rem & 0xFFFFu) ? 1u : 0u) << k;
+      const uint32_t rem = (uint32_t)d.rem & 0xFFFFu, below = (uint32_t)d.rem >> 16;
+      dst = gids[sub < rem ? d.at + sub : dead_at];
+      hm |= (sub >= below ? 1u : 0u) << k;
     } else {
       dst = gids[(int32_t)sub < d.rem ? d.at + sub : dead_at];
     }
@@ -581,7 +566,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : 1) query_c
         return SegRef<IDX>{at, (int32_t)(len - k)};
       } else {
         const uint32_t rem = min(len - k, 0xFFFFu), below = low > k ? min(low - k, rem) : 0u;
-        return SegRef<IDX>{at, (int32_t)((rem << 16) | below)};
+        return SegRef<IDX>{at, (int32_t)(rem | (below << 16))};
       }
     };
     const uint32_t nseg = (len + SEG - 1) / SEG;
@@ -819,7 +804,10 @@ static int query_form(const nq_index* ix, bool small) {
     if (!strcmp(env, "dual16") && query_dual_ok(ix)) return kFormDual16;
   }
   if (!seg_ok) return kFormStream;
-  if (small) return kFormStream;  // dual8/seg8 measured within 2% of it (L2 sector rate bound)
+  // small shards: seg8 with the three-deep ring.  stream / dual8 / seg16 measure within 3 % of it on a box
+  // where the L2 prefetch works as intended (0.63-0.65 ms at configs[1]); the deeper ring is the safer choice
+  // when it does not (one B200 of the pool ran the stream form at 1.04 ms, its lone-CTA time)
+  if (small) return kFormSeg8;
   return ix->n >= 40000 ? kFormSeg32 : kFormStream;
 }
 template <typename IT>
