@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-genomes", type=int, default=0, help="genomes per GPU in the e2e leg (default: all that fit host RAM)")
     ap.add_argument("--reads", type=int, default=0, help="c4: reads per GPU (default 10M)")
+    ap.add_argument("--query-groups", type=int, default=1,
+                    help="q100k: R query groups x (GPUs / R) genome shards; every shard is held by R GPUs, each counting 1/R of "
+                         "the queries (default 1 = the north-star layout, one gid shard per GPU)")
     ap.add_argument("--workload", default="c2", choices=["c2", "q100k", "c4", "c5"],
                     help="c2: the contract line (default).  q100k: secondary line, query sketches/s against a 100k-genome "
                          "index split over the GPUs (BASELINE metric, second half); genomes are sketched in batches.  "
@@ -235,14 +238,19 @@ def run_q100k(args):
         dist.init_process_group("nccl", device_id=dev)
     Gt = args.genomes or 100_000
     Qt = args.queries or 10_000
-    G, Q, L = Gt // world, Qt // world, args.genome_len
+    R = max(1, args.query_groups)
+    if world % R:
+        raise SystemExit("--query-groups must divide the number of GPUs")
+    shards = world // R                # genome shards; rank r holds shard r % shards and serves query group r // shards
+    shard, group = rank % shards, rank // shards
+    G, Q, L = Gt // shards, Qt // world, args.genome_len
     Lc = lib()
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx = niqki_b200.Context(local, stream)
     ix = niqki_b200.Index(S=S, K=K, W=W, H=H, min_fract=J, ctx=ctx)
     F = ix.F
-    g0, q0 = rank * G, rank * Q
+    g0, q0 = shard * G, rank * Q
     B = 4000
     buf = torch.empty(B * L + 64, dtype=torch.uint8, device=dev)
     sk_idx = torch.empty((G, F), dtype=torch.int32, device=dev)
@@ -273,10 +281,12 @@ def run_q100k(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    per_group = (Q * world) // R       # queries this rank counts: the group's slice of the all-gathered sketches
+
     def step():
         if world > 1:
             dist.all_gather_into_tensor(sk_all, sk_qry)
-        ix.query_sketches(sk_all, fetch=False)
+        ix.query_sketches(sk_all[group * per_group:(group + 1) * per_group] if R > 1 else sk_all, fetch=False)
 
     for _ in range(args.warmup):
         step()
@@ -306,7 +316,7 @@ def run_q100k(args):
     h_sk = torch.empty((Q * world, F), dtype=torch.int32, pin_memory=True)
     h_sk.copy_(sk_all)
     torch.cuda.synchronize()
-    n_sk = h_sk.numpy()
+    n_sk = h_sk.numpy()[group * per_group:(group + 1) * per_group] if R > 1 else h_sk.numpy()
     ptr, cnt, gid = ix.query_sketches(n_sk)
     barrier()
     t0 = time.perf_counter()
@@ -325,7 +335,7 @@ def run_q100k(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         nq_total = Q * world
-        q_bytes = 4 * gathered + nq_total * F * (8 + 2)
+        q_bytes = 4 * gathered + (per_group if R > 1 else nq_total) * F * (8 + 2)  # this rank's launch
         q_gbs = q_bytes / (q_ms / max(q_n, 1) / 1e3) / 1e9 if q_ms else None
         info = ix.info()
         line = {"metric": "query sketches/s vs 100k-genome index (10k mutated-copy queries, minjac 0.1)",
@@ -333,8 +343,10 @@ def run_q100k(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": {"workload": f"secondary (not the contract line): {Gt} synthetic {L} bp genomes indexed, gid-sharded over "
-                                       f"{world} GPU(s), {nq_total} mutated-copy queries all-gathered and counted on every shard",
-                           "K": K, "S": S, "W": W, "H": H, "minjac": J, "genomes_per_gpu": G, "queries_total": nq_total,
+                                       f"{world} GPU(s), {nq_total} mutated-copy queries all-gathered and counted on every shard"
+                                       + (f"; layout {shards} gid shards x {R} query groups (each shard held by {R} GPUs, each "
+                                          f"counting 1/{R} of the queries)" if R > 1 else ""),
+                           "K": K, "S": S, "W": W, "H": H, "minjac": J, "genomes_per_gpu": G, "queries_total": nq_total, "query_groups": R,
                            "l2": "per-step index traffic far larger than L2 (>= 1 GB of postings gathered per GPU)"},
                 "index_postings_per_gpu": info["n_postings"], "index_build_wall_s": t_build,
                 "roofline": {"kernel": "query_count_kernel", "bound": "hbm", "achieved": q_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -747,7 +747,7 @@ template <typename IT, int MODE, int NT, int SEG, int T, bool SPLIT = false>
 static cudaError_t launch_query_seg_t(size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st, int* occ) {
   const bool idx32 = (uint64_t)a.F * a.gid_stride + kQuerySlack < (1ull << 32);
   constexpr int R = NT <= 256 ? 4 : 8;
-  constexpr int D = NT <= 256 ? 3 : 2;
+  constexpr int D = NT <= 256 ? 3 : 2;  // registers: 64 per thread at 1024 and at 2 x 512 threads per SM
   constexpr unsigned QPC = MODE == kDual16 ? 2 : 1;  // queries per CTA
   // 64-bit posting indexes only occur with global counters (n > 131k at S=15), where shared memory is free
   auto k32 = query_count_seg_kernel<IT, MODE, NT, uint32_t, SEG, T, R, D, SPLIT>;
@@ -826,6 +826,8 @@ static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, un
     if (form == kFormDual8) return launch_query_seg_t<IT, kDual16, 256, 8, 64>(dsmem, nb, a, q0, st, occ);
     return launch_query_seg_t<IT, kDual16, 256, 16, 64>(dsmem, nb, a, q0, st, occ);
   }
+  // (256- / 512-thread CTAs, 4 / 2 per SM, for counter arrays of 26..100 KB were built and measured slower than
+  //  one 1024-thread CTA per SM: 16.6 vs 15.4 ms at 25k genomes, 21.6 vs 17.2 ms at 50k, 10k queries)
 #define NQ_SEG_DISPATCH(MODE)                                                                                      \
   if (small) {                                                                                                     \
     if (form == kFormSeg8) return launch_query_seg_t<IT, MODE, 128, 8, 64>(smem, nb, a, q0, st, occ);              \
@@ -833,8 +835,6 @@ static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, un
     if (form == kFormSeg32) return launch_query_seg_t<IT, MODE, 128, 32, 64>(smem, nb, a, q0, st, occ);            \
     return launch_query_t<IT, MODE, 128>(smem, nb, a, q0, st, occ);                                                \
   }                                                                                                                \
-  if (form == kFormSeg8) return launch_query_seg_t<IT, MODE, 1024, 8, 96>(smem, nb, a, q0, st, occ);               \
-  if (form == kFormSeg16) return launch_query_seg_t<IT, MODE, 1024, 16, 96>(smem, nb, a, q0, st, occ);             \
   if (form == kFormSeg32) return launch_query_seg_t<IT, MODE, 1024, 32, 96>(smem, nb, a, q0, st, occ);             \
   return launch_query_t<IT, MODE, 1024>(smem, nb, a, q0, st, occ);
   // 65.6k..131k genomes with packed counters: gather from the u16 copy of the postings

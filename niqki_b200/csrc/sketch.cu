@@ -49,6 +49,13 @@ struct KmerState {
 template <bool SMEM>
 struct SketchSink {
   uint32_t* sk;  // shared (SMEM) or global sketch row
+  // global form only: coarse shared-memory filter, `fbits` (0, 4 or 8) bits per cell holding an upper
+  // bound of the top bits (fp >> cshift) of the smallest fingerprint this CTA has SUBMITTED to the
+  // cell.  A k-mer whose top bits are above it cannot lower the cell and skips the global access.
+  // Updates are plain (racy) stores: a lost or stale update only leaves a bound that is too high,
+  // i.e. a more permissive filter — every value ever stored is the top bits of a submitted fingerprint.
+  uint8_t* filt;
+  uint32_t fbits, cshift;
   __device__ __forceinline__ void update(uint32_t b, uint32_t fp) const {
     // sketch[b] = min(sketch[b], fp) with empty = 0xFFFFFFFF (:350-355).
     if (SMEM) {
@@ -56,7 +63,16 @@ struct SketchSink {
       // conditional atomic (measured on B200: 563 vs 517 Gbases/s)
       atomicMin(&sk[b], fp);
     } else {
-      // global memory: a plain read filters out the ~95% of k-mers that cannot lower the cell; a
+      if (fbits == 8) {
+        const uint32_t c = min(fp >> cshift, 255u), cur = filt[b];
+        if (c > cur) return;
+        if (c < cur) filt[b] = (uint8_t)c;
+      } else if (fbits == 4) {
+        const uint32_t byte = filt[b >> 1], sh = (b & 1u) * 4u, cur = (byte >> sh) & 15u, c = min(fp >> cshift, 15u);
+        if (c > cur) return;
+        if (c < cur) filt[b >> 1] = (uint8_t)((byte & ~(15u << sh)) | (c << sh));
+      }
+      // global memory: a plain read filters out the k-mers that cannot lower the cell; a
       // stale read only makes the filter conservative because cells never increase
       if (fp < sk[b]) atomicMin(&sk[b], fp);
     }
@@ -114,8 +130,10 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __res
   uint32_t* grow = gsk + (size_t)entry * P.F;
   if (SMEM)
     for (uint32_t i = threadIdx.x; i < P.F; i += NT) ssk[i] = kEmpty;
+  else
+    for (uint32_t i = threadIdx.x; i < P.F * P.filter / 32; i += NT) ssk[i] = 0xFFFFFFFFu;  // filter: "anything may still win"
   __syncthreads();
-  SketchSink<SMEM> sink{SMEM ? ssk : grow};
+  SketchSink<SMEM> sink{SMEM ? ssk : grow, reinterpret_cast<uint8_t*>(ssk), P.filter, P.filter ? P.W - P.filter : 0u};
 
   // this thread's run of k-mer starts [lo, hi): 16-byte aligned slices of the span
   const uint64_t base = A & ~15ull;
@@ -415,7 +433,7 @@ using namespace nq;
 template <bool SMEM, int NT, bool RC_HI, bool SMALL_REM, bool DEF>
 static int launch_scan_t(nq_ctx* ctx, const DevParams& P, const uint8_t* d_bases, const uint64_t* d_offsets,
                          const Span* d_spans, uint64_t nblocks, uint32_t* d_sk) {
-  const size_t smem = SMEM ? (size_t)P.F * 4 : 0;
+  const size_t smem = SMEM ? (size_t)P.F * 4 : (size_t)P.F * P.filter / 8;  // sketch, or the coarse filter of the global form
   auto kern = sketch_scan_kernel<SMEM, NT, RC_HI, SMALL_REM, DEF>;
   NQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NqTimer timer(ctx, NQK_SCAN);
@@ -524,12 +542,21 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
   const bool fits = 2048 + 1024 + (size_t)P.F * 4 <= ctx->smem_optin;  // + static LUT + driver reserve
   const bool small = total_k / std::max<uint64_t>(nblocks, 1) < 16384;  // short entries: small CTAs
   int st;
-  if (fits)
+  if (fits) {
     st = small ? launch_scan<true, 128>(ctx, P, b, d_offsets, d_spans, nblocks, sk)
                : launch_scan<true, 1024>(ctx, P, b, d_offsets, d_spans, nblocks, sk);
-  else
-    st = small ? launch_scan<false, 128>(ctx, P, b, d_offsets, d_spans, nblocks, sk)
-               : launch_scan<false, 1024>(ctx, P, b, d_offsets, d_spans, nblocks, sk);
+  } else {
+    // the sketch stays in HBM/L2; a coarse filter (8 or 4 bits per cell) takes the shared memory instead
+    DevParams PG = P;
+    static const char* env = getenv("NQ_SCAN_FILTER");  // "0": no filter (measurement only)
+    const size_t room = ctx->smem_optin - 2048 - 1024;
+    if (!small && !(env && env[0] == '0')) {
+      if (P.W >= 8 && (size_t)P.F <= room) PG.filter = 8;
+      else if (P.W >= 4 && (size_t)P.F / 2 <= room) PG.filter = 4;
+    }
+    st = small ? launch_scan<false, 128>(ctx, PG, b, d_offsets, d_spans, nblocks, sk)
+               : launch_scan<false, 1024>(ctx, PG, b, d_offsets, d_spans, nblocks, sk);
+  }
   nq_dfree(ctx, d_offsets);
   nq_dfree(ctx, d_spans);
   NQ_TRY(st);

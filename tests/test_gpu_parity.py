@@ -93,9 +93,9 @@ def test_sketch_long_sliced_and_batched(nb, ctx):
 def test_sketch_large_S_global_path(nb, ctx):
     """S > 15: the sketch no longer fits in shared memory."""
     rng = np.random.default_rng(12)
-    for S, W in [(16, 12), (18, 12)]:
-        o = oracle(K=31, S=S, W=W, H=4)
-        g = gpu_index(nb, ctx, K=31, S=S, W=W, H=4)
+    for S, W, H, K in [(16, 12, 4, 31), (18, 12, 4, 31), (17, 9, 3, 21), (16, 6, 2, 31)]:  # 8-bit / 4-bit coarse filter, generic parameters
+        o = oracle(K=K, S=S, W=W, H=H)
+        g = gpu_index(nb, ctx, K=K, S=S, W=W, H=H)
         seqs = [random_dna(rng, 2_000_000), random_dna(rng, 300_000)]
         sks, _ = g.sketch_many(seqs)
         assert np.array_equal(sks, o.sketch_many(seqs))
@@ -292,7 +292,7 @@ def test_sharded_query_equals_single(nb, ctx):
         assert np.array_equal(merged, (c[seg].astype(np.uint64) << np.uint64(32)) | gid[seg])
 
 
-@pytest.mark.parametrize("n", [5_000, 30_000, 65_400, 70_000])
+@pytest.mark.parametrize("n", [5_000, 20_000, 30_000, 65_400, 70_000])
 def test_index_build_synthetic_sketches(nb, ctx, n):
     """Index build on raw sketches: skewed fingerprints, lists far longer than a warp (clusters of
     identical genomes), unposted cells (-1 and fp >= 2^W), u16 -> u32 id switch at 65400."""
