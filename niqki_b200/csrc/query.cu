@@ -30,6 +30,13 @@
 
 namespace nq {
 
+// posting gathers of the segment-table form: NQ_GATHER_CG builds them as ld.global.cg (no L1 allocation)
+#ifdef NQ_GATHER_CG
+#define NQ_GATHER(p) __ldcg(p)
+#else
+#define NQ_GATHER(p) (*(p))
+#endif
+
 struct QueryArgs {
   const int32_t* qsk;  // [nq][F]
   const void* dir;     // [F][row_stride] packed {begin,end} (u16 pair in a u32, or uint2)
@@ -48,6 +55,7 @@ struct QueryArgs {
   uint32_t prefetch;    // cooperative L2 prefetch of upcoming cells (only when a few chunks of cells fit in L2)
   const uint4* dir3;       // split16 side arrays of the index (internal.h), or null
   const uint16_t* gids16;
+  uint64_t nq_total;    // queries of the whole call (CTA size of the small-shard form)
   uint64_t q_end;       // one past the last query of the launch (kDual16: a CTA's second query may not exist)
   uint32_t* dense;      // when set: row q of [nq][n] takes every genome's count instead of the thresholded hit list (--matrix)
 };
@@ -247,7 +255,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 9 : 1) query_count_kernel(Quer
   PfSlice pf{};
   if (warp == 0 && a.prefetch) {
     pf = make_pf_slice(a, sizeof(IT), lane);
-    for (uint32_t ch = 0; ch < kPfAhead; ++ch) prefetch_chunk(a, pf, ch);
+    for (uint32_t ch = 0; ch < a.prefetch; ++ch) prefetch_chunk(a, pf, ch);
   }
   for (uint32_t i = tid; i < words; i += NT) cnt[i] = 0;
   __syncthreads();
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 9 : 1) query_count_kernel(Quer
   };
   for (; c_cur < a.F; c_cur += step) {
     const uint32_t cell = c_cur + lane;
-    if (warp == 0 && a.prefetch && c_cur % kPfCells == 0) prefetch_chunk(a, pf, c_cur / kPfCells + kPfAhead);
+    if (warp == 0 && a.prefetch && c_cur % kPfCells == 0) prefetch_chunk(a, pf, c_cur / kPfCells + a.prefetch);
     // prefetch: fingerprint of group +2, directory word of group +1
     fp_next2 = 0xFFFFFFFFu;
     if (c_cur + 2 * step + lane < a.F) fp_next2 = (uint32_t)__ldg(&sk[c_cur + 2 * step + lane]);
@@ -448,7 +456,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : 1) query_c
   PfSlice pf{};
   if (warp == 0 && a.prefetch) {
     pf = make_pf_slice(a, sizeof(IT), lane);
-    for (uint32_t ch = 0; ch < kPfAhead; ++ch) prefetch_chunk(a, pf, ch);
+    for (uint32_t ch = 0; ch < a.prefetch; ++ch) prefetch_chunk(a, pf, ch);
   }
   const bool shared_q = MODE == kGlobal32 && a.parts != 0;  // counters zeroed by the host, finished by query_finish_kernel
   if (!shared_q)
@@ -517,10 +525,10 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : 1) query_c
     const SegRef<IDX> d = t[k * SPR + grp];
     if (SPLIT) {
       const uint32_t rem = (uint32_t)d.rem & 0xFFFFu, below = (uint32_t)d.rem >> 16;
-      dst = gids[sub < rem ? d.at + sub : dead_at];
+      dst = NQ_GATHER(&gids[sub < rem ? d.at + sub : dead_at]);
       hm |= (sub >= below ? 1u : 0u) << k;
     } else {
-      dst = gids[(int32_t)sub < d.rem ? d.at + sub : dead_at];
+      dst = NQ_GATHER(&gids[(int32_t)sub < d.rem ? d.at + sub : dead_at]);
     }
   };
   // gather nb (1..R, warp-uniform) rounds starting at table position t0 (a multiple of SPR)
@@ -549,7 +557,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : 1) query_c
   };
   for (; c_cur < F; c_cur += step) {
     const uint32_t cell = c_cur + lane;
-    if (warp == 0 && a.prefetch && c_cur % kPfCells == 0) prefetch_chunk(a, pf, c_cur / kPfCells + kPfAhead);
+    if (warp == 0 && a.prefetch && c_cur % kPfCells == 0) prefetch_chunk(a, pf, c_cur / kPfCells + a.prefetch);
     fp_next2 = 0xFFFFFFFFu;
     if (c_cur + 2 * step + lane < F) fp_next2 = (uint32_t)__ldg(&sk[c_cur + 2 * step + lane]);
     probe(dw_next, cell + step, fp_next);
@@ -828,8 +836,19 @@ static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, un
   }
   // (256- / 512-thread CTAs, 4 / 2 per SM, for counter arrays of 26..100 KB were built and measured slower than
   //  one 1024-thread CTA per SM: 16.6 vs 15.4 ms at 25k genomes, 21.6 vs 17.2 ms at 50k, 10k queries)
+  // small shards: 128-thread CTAs, 8-9 queries per SM — unless their counters leave the SM less than ~24 KB of
+  // L1 to track the gathers (12.5k genomes: 8 x 26.9 KB of shared memory), or the batch is many waves long;
+  // then 256-thread CTAs (4 queries per SM, 8 warps each: the same 32 warps on half the shared memory).
+  // 12.5k genomes x 10k queries: 11.8 -> 6.65 ms; 10k x 10k: 6.63 -> 5.94 ms; but 10k x 2k: 1.29 -> 1.40 ms and
+  // 10k x 1k: 0.64 -> 0.70 ms (half-empty waves), which stay on 128 threads.  NQ_QUERY_NT overrides.
+  static const char* nt_env = getenv("NQ_QUERY_NT");
+  const size_t cta128 = smem + 1024 + 800;  // dynamic + per-CTA reserve + static tables
+  const size_t occ128 = std::min<size_t>(8, (228 * 1024) / cta128);
+  const bool l1_starved = 228 * 1024 - occ128 * cta128 < 24 * 1024;
+  const bool nt256 = nt_env ? atoi(nt_env) == 256 : (l1_starved || a.nq_total >= (uint64_t)ix->ctx->sm_count * 36);
 #define NQ_SEG_DISPATCH(MODE)                                                                                      \
   if (small) {                                                                                                     \
+    if (form == kFormSeg8 && nt256) return launch_query_seg_t<IT, MODE, 256, 8, 64>(smem, nb, a, q0, st, occ);     \
     if (form == kFormSeg8) return launch_query_seg_t<IT, MODE, 128, 8, 64>(smem, nb, a, q0, st, occ);              \
     if (form == kFormSeg16) return launch_query_seg_t<IT, MODE, 128, 16, 64>(smem, nb, a, q0, st, occ);            \
     if (form == kFormSeg32) return launch_query_seg_t<IT, MODE, 128, 32, 64>(smem, nb, a, q0, st, occ);            \
@@ -850,6 +869,15 @@ static cudaError_t launch_query(const nq_index* ix, int mode, size_t smem, unsig
                        : launch_query_it<uint32_t>(ix, mode, smem, nb, a, q0, st, occ);
 }
 
+// Chunks of lead of the cooperative L2 prefetch (0 = off): the window of lead + 1 chunks of kPfCells cells
+// (directory rows + posting arrays) must sit in L2.  NQ_QUERY_PF_AHEAD overrides the lead (measurement only).
+static uint32_t query_prefetch_lead(const nq_index* ix) {
+  static const char* env = getenv("NQ_QUERY_PF_AHEAD");
+  const uint32_t lead = env ? (uint32_t)atoi(env) : kPfAhead;
+  const uint64_t chunk = (uint64_t)kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem;
+  return (lead + 1) * chunk <= (64ull << 20) ? lead : 0u;
+}
+
 // Queries per launch.  Global counters bound it by memory.  When the L2 prefetch is on (a few
 // chunks of cells fit in L2: the co-resident CTAs share what each of them pulls in, as long as
 // they sweep the cells in step), more queries than CTA slots are cut into equal launches of at most
@@ -866,6 +894,8 @@ static uint64_t query_wave(const nq_index* ix, int mode, size_t smem, const Quer
   if (!a.prefetch || (env && env[0] == '0')) return nq;
   int occ = 0;
   if (launch_query(ix, mode, smem, 1, a, 0, nullptr, &occ) != cudaSuccess || occ <= 0) return nq;
+  static const char* cap_env = getenv("NQ_QUERY_WAVE_SM");  // cap of resident queries per SM in a wave (measurement only)
+  if (cap_env && atoi(cap_env) > 0) occ = std::min(occ, atoi(cap_env));
   const uint64_t slots = (uint64_t)occ * ix->ctx->sm_count;
   if (nq <= slots) return nq;
   const uint64_t waves = (nq + slots - 1) / slots;
@@ -938,6 +968,7 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
   a.F = p.F; a.range = (uint32_t)p.range; a.n = ix->n; a.row_stride = ix->row_stride; a.gid_stride = ix->gid_stride;
   a.gid_base = ix->gid_base;
   a.dir3 = ix->d_dir3; a.gids16 = ix->d_gids16;
+  a.nq_total = nq;
   a.min_score = min_score;
   a.wrap_mask = p.S <= 7 ? 0xFFu : p.S <= 15 ? 0xFFFFu : 0xFFFFFFFFu;  // counter widths of :635/:651/:667
 
@@ -945,7 +976,7 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
   size_t smem;
   query_layout(ix, mode, smem);
   // the prefetch window (kPfAhead + 1 chunks of kPfCells cells: directory rows + posting arrays) must sit in L2
-  a.prefetch = (uint64_t)(kPfAhead + 1) * kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem <= (64ull << 20);
+  a.prefetch = query_prefetch_lead(ix);
 
   const uint64_t q_per_launch = query_wave(ix, mode, smem, a, nq);
   if (set_query_parts(ix, mode, q_per_launch, a) != NQ_OK) { nq_dfree(ctx, a.slice_hits); delete hits; return NQ_ERR_CUDA; }
@@ -1050,12 +1081,13 @@ int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, ui
   a.F = p.F; a.range = (uint32_t)p.range; a.n = ix->n; a.row_stride = ix->row_stride; a.gid_stride = ix->gid_stride;
   a.gid_base = ix->gid_base;
   a.dir3 = ix->d_dir3; a.gids16 = ix->d_gids16;
+  a.nq_total = nq;
   a.wrap_mask = wrap_mask;
   a.dense = d_out;
   int mode;
   size_t smem;
   query_layout(ix, mode, smem);
-  a.prefetch = (uint64_t)(kPfAhead + 1) * kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem <= (64ull << 20);
+  a.prefetch = query_prefetch_lead(ix);
   const uint64_t q_per_launch = query_wave(ix, mode, smem, a, nq);
   if (set_query_parts(ix, mode, q_per_launch, a) != NQ_OK) { nq_dfree(ctx, a.slice_hits); return NQ_ERR_CUDA; }
   unsigned long long* d_cursor = nullptr;  // [1] = gather statistics
