@@ -30,13 +30,6 @@
 
 namespace nq {
 
-// posting gathers of the segment-table form: NQ_GATHER_CG builds them as ld.global.cg (no L1 allocation)
-#ifdef NQ_GATHER_CG
-#define NQ_GATHER(p) __ldcg(p)
-#else
-#define NQ_GATHER(p) (*(p))
-#endif
-
 struct QueryArgs {
   const int32_t* qsk;  // [nq][F]
   const void* dir;     // [F][row_stride] packed {begin,end} (u16 pair in a u32, or uint2)
@@ -525,10 +518,10 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : 1) query_c
     const SegRef<IDX> d = t[k * SPR + grp];
     if (SPLIT) {
       const uint32_t rem = (uint32_t)d.rem & 0xFFFFu, below = (uint32_t)d.rem >> 16;
-      dst = NQ_GATHER(&gids[sub < rem ? d.at + sub : dead_at]);
+      dst = gids[sub < rem ? d.at + sub : dead_at];
       hm |= (sub >= below ? 1u : 0u) << k;
     } else {
-      dst = NQ_GATHER(&gids[(int32_t)sub < d.rem ? d.at + sub : dead_at]);
+      dst = gids[(int32_t)sub < d.rem ? d.at + sub : dead_at];
     }
   };
   // gather nb (1..R, warp-uniform) rounds starting at table position t0 (a multiple of SPR)
