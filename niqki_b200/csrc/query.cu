@@ -427,7 +427,8 @@ struct SegRef {
 // half-words: lanes at or past the second number are "high", which includes the dead lanes of a
 // list's last round — their dummy id is stored minus 2^16.
 template <typename IT, int MODE, int NT, typename IDX, int SEG, int T, int R, int D, bool SPLIT = false>
-__global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : 1) query_count_seg_kernel(QueryArgs a, uint64_t q0) {
+__global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : (NT == 512 && MODE != kGlobal32) ? 2 : 1)
+query_count_seg_kernel(QueryArgs a, uint64_t q0) {
   static_assert(!SPLIT || (SEG == 32 && MODE == kPack16 && sizeof(IT) == 2 && sizeof(IDX) == 4), "split16 form");
   constexpr int SPR = 32 / SEG;  // segments per round
   constexpr bool DUAL = MODE == kDual16;
@@ -827,8 +828,15 @@ static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, un
     if (form == kFormDual8) return launch_query_seg_t<IT, kDual16, 256, 8, 64>(dsmem, nb, a, q0, st, occ);
     return launch_query_seg_t<IT, kDual16, 256, 16, 64>(dsmem, nb, a, q0, st, occ);
   }
-  // (256- / 512-thread CTAs, 4 / 2 per SM, for counter arrays of 26..100 KB were built and measured slower than
-  //  one 1024-thread CTA per SM: 16.6 vs 15.4 ms at 25k genomes, 21.6 vs 17.2 ms at 50k, 10k queries)
+  // shards between "small" and "one CTA per SM": four 256-thread CTAs per SM while their counters + tables
+  // leave >= 40 KB of L1 (n <= ~20k packed), two 512-thread CTAs while they leave >= 48 KB (n <= ~38k).  10k
+  // queries vs 16k / 20k / 25k / 35k genomes: 12.9 / ~14 / 15.5 / 18.3 ms as one 1024-thread CTA per SM ->
+  // 8.1 / 10.5 / 13.3 / 16.6 ms.  Sized WITHOUT regard for L1 (256 threads up to 51 KB, 512 up to 100 KB) the
+  // same kernels were slower than the 1024-thread form (16.6 vs 15.4 ms at 25k, 21.6 vs 17.2 ms at 50k).
+  static const char* mid_env = getenv("NQ_QUERY_MID");  // "0": the 1024-thread forms (measurement only)
+  const bool mid_on = !(mid_env && mid_env[0] == '0');
+  const bool mid256 = mid_on && !small && 4 * (smem + 1024 + 4400) + 40 * 1024 <= 228 * 1024;
+  const bool mid512 = mid_on && !small && !mid256 && 2 * (smem + 1024 + 12600) + 48 * 1024 <= 228 * 1024;
   // small shards: 128-thread CTAs, 8-9 queries per SM — unless their counters leave the SM less than ~24 KB of
   // L1 to track the gathers (12.5k genomes: 8 x 26.9 KB of shared memory), or the batch is many waves long;
   // then 256-thread CTAs (4 queries per SM, 8 warps each: the same 32 warps on half the shared memory).
@@ -847,6 +855,8 @@ static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, un
     if (form == kFormSeg32) return launch_query_seg_t<IT, MODE, 128, 32, 64>(smem, nb, a, q0, st, occ);            \
     return launch_query_t<IT, MODE, 128>(smem, nb, a, q0, st, occ);                                                \
   }                                                                                                                \
+  if (mid256) return launch_query_seg_t<IT, MODE, 256, 16, 64>(smem, nb, a, q0, st, occ);                          \
+  if (mid512) return launch_query_seg_t<IT, MODE, 512, 16, 96>(smem, nb, a, q0, st, occ);                          \
   if (form == kFormSeg32) return launch_query_seg_t<IT, MODE, 1024, 32, 96>(smem, nb, a, q0, st, occ);             \
   return launch_query_t<IT, MODE, 1024>(smem, nb, a, q0, st, occ);
   // 65.6k..131k genomes with packed counters: gather from the u16 copy of the postings
