@@ -325,16 +325,23 @@ __global__ void __launch_bounds__(NT) densify_kernel(uint32_t* gsk, DevParams P,
 // same lowest-index-source rule as densify_kernel) runs on the warp with the two hash_family
 // terms of every cell cached beside it (they are functions of the cell's value, copied along).
 // ------------------------------------------------------------------------------------------
-template <int NW>
+// LISTED: densification walks a dense list of the initially non-empty cells {value, cached hash terms, lowest
+// index holding the value so far} instead of all F cells: every holder of a value aims at the same target, so
+// only the lowest-index holder matters (it is what the reference's in-order scan lets win), and a value that
+// fills a cell just lowers its entry's index if the new cell lies below it.  ~95 entries instead of 256 cells
+// per pass for a 150 bp read at S=8, and no resolve sweep: the winner of a target recognises its own mark.
+template <int NW, bool LISTED>
 __global__ void __launch_bounds__(NW * 32) sketch_reads_kernel(const uint8_t* __restrict__ bases,
                                                                const uint64_t* __restrict__ offsets, uint64_t n,
                                                                uint32_t* __restrict__ gsk, DevParams P,
                                                                uint32_t* __restrict__ flags) {
-  extern __shared__ __align__(16) uint32_t smem[];  // per warp: sk[F] | ab[F] ({family_a, family_b} as two u16)
+  extern __shared__ __align__(16) uint32_t smem[];  // per warp: sk[F] | ab[F] ({family_a, family_b} as two u16) [| lv[F] | lidx[F]]
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t F = P.F, Fmask = F - 1, K = P.K;
-  uint32_t* sk = smem + (size_t)warp * 2 * F;
-  uint32_t* ab = sk + F;
+  uint32_t* sk = smem + (size_t)warp * (LISTED ? 4 : 2) * F;
+  uint32_t* ab = sk + F;      // cell-indexed (cell form) or entry-indexed (listed form)
+  uint32_t* lv = ab + F;      // listed form: value of entry e
+  uint32_t* lidx = lv + F;    // listed form: lowest index of a cell holding that value
   constexpr unsigned kFull = 0xFFFFFFFFu;
   for (uint64_t entry = (uint64_t)blockIdx.x * NW + warp; entry < n; entry += (uint64_t)gridDim.x * NW) {
     const uint64_t E0 = offsets[entry], L = offsets[entry + 1] - E0;
@@ -368,16 +375,58 @@ __global__ void __launch_bounds__(NW * 32) sketch_reads_kernel(const uint8_t* __
     }
     __syncwarp();
     // ---- densification
-    uint32_t my_empty = 0;
-    for (uint32_t i = lane; i < F; i += 32) {
-      const uint32_t v = sk[i];
-      if (v == kEmpty) ++my_empty;
-      else ab[i] = family_a(v, Fmask) | (family_b(v, Fmask) << 16);
+    uint32_t my_empty = 0, n_ent = 0;
+    for (uint32_t i0 = 0; i0 < F; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      const bool in = i < F;  // F < 32 when S < 5
+      const uint32_t v = in ? sk[i] : kEmpty;
+      const bool full = in && v != kEmpty;
+      if (in && !full) ++my_empty;
+      if (LISTED) {
+        const unsigned bal = __ballot_sync(kFull, full);
+        if (full) {
+          const uint32_t e = n_ent + __popc(bal & ((1u << lane) - 1));
+          lv[e] = v;
+          lidx[e] = i;
+          ab[e] = family_a(v, Fmask) | (family_b(v, Fmask) << 16);
+        }
+        n_ent += __popc(bal);
+      } else if (full) {
+        ab[i] = family_a(v, Fmask) | (family_b(v, Fmask) << 16);
+      }
     }
     uint32_t empty = __reduce_add_sync(kFull, my_empty);
     uint32_t fl = 0;
     if (empty == F) {
       fl = NQ_ENTRY_SKIPPED;  // nothing was sketched (len <= K)
+    } else if (empty && LISTED) {
+      __syncwarp();
+      uint32_t step = 0, idle = 0;
+      while (empty != 0 && idle < F) {
+        for (uint32_t e = lane; e < n_ent; e += 32) {  // every entry marks its target with its lowest holder's index
+          const uint32_t h = ab[e];
+          const uint32_t t = ((h & 0xFFFFu) + step * (h >> 16)) & Fmask;
+          if (sk[t] >= kTent) atomicMin(&sk[t], kTent | lidx[e]);
+        }
+        __syncwarp();
+        uint32_t filled = 0;
+        for (uint32_t e = lane; e < n_ent; e += 32) {  // the entry whose mark survived fills the cell
+          const uint32_t h = ab[e];
+          const uint32_t t = ((h & 0xFFFFu) + step * (h >> 16)) & Fmask;
+          const uint32_t mine = lidx[e];
+          if (sk[t] == (kTent | mine)) {
+            sk[t] = lv[e];
+            if (t < mine) lidx[e] = t;
+            ++filled;
+          }
+        }
+        const uint32_t got = __reduce_add_sync(kFull, filled);
+        __syncwarp();
+        empty -= got;
+        idle = got ? 0 : idle + 1;
+        ++step;
+      }
+      if (empty) fl = NQ_ENTRY_DENSIFY_STALLED;
     } else if (empty) {
       __syncwarp();
       uint32_t step = 0, idle = 0;
@@ -489,20 +538,26 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
   if (!h_rec_entry && longest + p->K <= 4096 && P.S <= 11 && P.K <= 32) {
     static const char* env = getenv("NQ_READS_KERNEL");  // "0": the CTA-per-entry kernels (measurement only)
     if (!(env && env[0] == '0')) {
-      constexpr int NW = 8;
-      const size_t smem = (size_t)NW * 2 * P.F * 4;
+      static const char* dens_env = getenv("NQ_READS_DENSIFY");  // "cell": the all-cells densification (measurement only)
+      const bool listed = !(dens_env && dens_env[0] == 'c');
       uint64_t* d_offsets = nullptr;
       NQ_TRY(nq_dmalloc(ctx, (void**)&d_offsets, (n + 1) * sizeof(uint64_t)));
       NQ_CUDA(cudaMemcpyAsync(d_offsets, h_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-      NQ_CUDA(cudaFuncSetAttribute(sketch_reads_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int per_sm = 1;
-      NQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_reads_kernel<NW>, NW * 32, smem));
-      const unsigned grid = (unsigned)std::min<uint64_t>((n + NW - 1) / NW, (uint64_t)ctx->sm_count * std::max(per_sm, 1));
-      {
+      auto launch = [&](auto kern, int nw, size_t smem) -> int {
+        NQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        NQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nw * 32, smem));
+        const unsigned grid = (unsigned)std::min<uint64_t>((n + nw - 1) / nw, (uint64_t)ctx->sm_count * std::max(per_sm, 1));
         NqTimer timer(ctx, NQK_SCAN);
-        sketch_reads_kernel<NW><<<grid, NW * 32, smem, ctx->stream>>>(reinterpret_cast<const uint8_t*>(d_bases), d_offsets, n,
-                                                                       reinterpret_cast<uint32_t*>(d_sketches), P, d_flags);
-      }
+        kern<<<grid, nw * 32, smem, ctx->stream>>>(reinterpret_cast<const uint8_t*>(d_bases), d_offsets, n,
+                                                   reinterpret_cast<uint32_t*>(d_sketches), P, d_flags);
+        return NQ_OK;
+      };
+      int lst;
+      if (!listed) lst = launch(sketch_reads_kernel<8, false>, 8, (size_t)8 * 2 * P.F * 4);
+      else if (P.F <= 1024) lst = launch(sketch_reads_kernel<8, true>, 8, (size_t)8 * 4 * P.F * 4);
+      else lst = launch(sketch_reads_kernel<4, true>, 4, (size_t)4 * 4 * P.F * 4);
+      if (lst != NQ_OK) { nq_dfree(ctx, d_offsets); return lst; }
       ctx->launches++;
       const cudaError_t le = cudaPeekAtLastError();
       nq_dfree(ctx, d_offsets);
