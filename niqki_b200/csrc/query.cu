@@ -1,24 +1,28 @@
 // query.cu — K4a: posting-list gather + per-genome hit counting + fused min_score threshold and
 // compaction.  Replaces Index::query_sketch (/root/reference/src/niqki_index.cpp:633-687).
 //
-// One CTA per query sketch; all queries of a batch are resident at once where shared memory allows
-// (256-thread CTAs, 8 per SM), so the wave sweeps the cells roughly in step and a cell's directory
-// and lists are served from L2 after their first touch.  The per-genome counters of the shard live
-// in shared memory (two 16-bit counters per word when S <= 15, because a count can never exceed
-// F = 2^S <= 32768 — the same widths the reference uses, :635-683).
-//
-// The gather is bound by the L1TEX tag stage (one cache line per cycle per SM for divergent
-// loads), not by bytes, so it is organised to touch as few (line, instruction) pairs as possible:
-// a warp takes 32 consecutive cells, every lane reads its cell's fingerprint (coalesced) and ONE
-// packed directory word {begin,end}; the 32 lists are then treated as one concatenated stream
-// that the whole warp walks 32 postings at a time — lanes reading neighbouring postings of one list
-// share a cache line, no lane idles on a short list, and every shared-memory atomicAdd carries 32
-// useful lanes.  The owner of stream slot s is found without a search: the lanes whose list starts
-// inside the current 32-slot round set one bit each (REDUX.OR), and a population count of the
-// bits at or below a slot gives the owner's rank among the non-empty lists.
-// The threshold pass then compacts (count, gid) pairs in gid order into a global pool (one
-// atomicAdd per query reserves the segment).  Sorting by (count, gid) descending (:685) is done by
-// the host when it merges shards.
+// One CTA per query sketch.  The per-genome counters of the shard live in shared memory (two 16-bit
+// counters per word when S <= 15, because a count can never exceed F = 2^S <= 32768 — the same
+// widths the reference uses, :635-683), or in HBM/L2 when the shard is too large for that.  A warp
+// takes 32 consecutive cells: every lane reads its cell's fingerprint (coalesced, two groups ahead)
+// and ONE packed directory word {begin,end} (one group ahead); the 32 lists are then gathered 32
+// postings per round through a register ring (the batch gathered before is counted while the next
+// one's loads fly).  Two gather forms share that frame:
+//   * query_count_kernel ("stream"): the 32 lists are one concatenated stream; the owner of a
+//     stream slot is found per round without a search (REDUX.OR of the lists that start inside the
+//     round + POPC of the bits at or below the slot);
+//   * query_count_seg_kernel ("segment table"): the lists are cut into segments of 8 / 16 / 32
+//     postings whose descriptors each cell's lane writes into a per-warp shared-memory table; a
+//     round is then one broadcast LDS + a few ALU instructions + the load.  Variants: split16 (u16
+//     copy of the postings for shards of 65.6k..131k genomes), many CTAs per query with global
+//     counters, two queries per CTA (measured, not default).
+// Which form, CTA size and segment size run is decided in launch_query_it from the counter footprint
+// — the L1 that the shared-memory counters leave is what tracks the gathers, DESIGN.md 4 — and the
+// batch size; co-resident CTAs of a small shard additionally pull upcoming cells into L2 with bulk
+// prefetches and are launched one resident wave at a time so that they sweep the cells in step.
+// The threshold pass compacts (count, gid) pairs in gid order into a global pool (one atomicAdd per
+// query reserves the segment), or writes the whole counter row (--matrix).  Sorting by (count, gid)
+// descending (:685) is done by the host when it merges shards.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
