@@ -75,7 +75,8 @@ uint64_t nq_ctx_launch_count(const nq_ctx* ctx);
 /* Profiling support: when on, every kernel family launched through the context is bracketed by
  * CUDA events on the launching stream.  nq_ctx_timing() synchronises and returns the accumulated
  * device milliseconds and launch count of one family since the last reset, kind = 0 scan
- * (hash + bucket-min), 1 densify, 2 transpose, 3 cell sort (CSR build), 4 query count, 5 matrix. */
+ * (hash + bucket-min), 1 densify, 2 transpose, 3 cell sort (CSR build), 4 query count, 5 matrix,
+ * 6 granule copy of the postings for the query kernel (slab). */
 int nq_ctx_set_timing(nq_ctx* ctx, int on);
 int nq_ctx_timing(nq_ctx* ctx, int kind, double* ms, uint64_t* launches);
 int nq_ctx_timing_reset(nq_ctx* ctx);
@@ -160,6 +161,40 @@ void nq_hits_free(nq_hits* h);
  * reproduces the reference's uint16_t counters (value mod 65536); thresholding and
  * formatting stay on the host (:600-608, :747-763). */
 int nq_matrix_rows(nq_index* ix, uint32_t row_begin, uint32_t row_end, int wrap16, uint32_t* counts);
+
+/* One tile of the genome x genome grid (--matrix over a gid-sharded index).  The
+ * reference derives the matrix from the posting lists alone (src/niqki_index.cpp:570-598); here the
+ * sketches of a row block are rebuilt from the shard that owns them (nq_index_sketches_device, rows
+ * local to the shard), handed to every shard (nq_bcast_sketches), and each shard counts them against
+ * its own columns: counts[r*n_shard + j], same wrap16 rule as nq_matrix_rows. */
+int nq_index_sketches_device(nq_index* ix, uint32_t row_begin, uint32_t row_end, int32_t* d_sketches);
+int nq_matrix_tile(nq_index* ix, const int32_t* d_row_sketches, uint32_t nrows, int wrap16, uint32_t* counts);
+
+/* ---- multi-GPU: the sharded index ------------------------------------------ */
+/* The reference is one address space (its callers insert_file_of_file_whole :461-500,
+ * query_file_of_file_whole :523-540 and query_matrix :614-628 become multi-GPU here).  The index
+ * shards by genome id in contiguous blocks (nq_shard_range), every shard is an ordinary nq_index
+ * with its own gid_base on its own device; the one exchange step is an all-gather of the query
+ * sketches over NCCL (u16 on the wire when W <= 15: cells outside [0, 2^W) are never probed, :655,
+ * and come back as -1), after which every shard counts every query and the host merges the
+ * per-shard hit lists — disjoint in gid, so concatenate + sort == the reference's order (:685).
+ * A communicator belongs to one context; collective calls are made by every rank, each from the
+ * thread that drives its context, and run on the context's stream.  NCCL is loaded at run time. */
+typedef struct nq_comm nq_comm;
+int nq_comm_unique_id(void* id128);  /* 128 bytes, made on rank 0 and handed to the other ranks */
+int nq_comm_init_rank(nq_ctx* ctx, const void* id128, int nranks, int rank, nq_comm** out);
+/* one process driving n devices: out[n] communicators, rank i on ctxs[i] */
+int nq_comm_init_all(nq_ctx* const* ctxs, int n, nq_comm** out);
+int nq_comm_destroy(nq_comm* c);
+int nq_comm_info(const nq_comm* c, int* rank, int* nranks, int* nccl_version);
+int nq_shard_range(uint64_t n, int nranks, int rank, uint64_t* begin, uint64_t* end);
+/* every rank contributes n_local sketches int32[n_local][F] (device); all receive
+ * int32[nranks*n_local][F] in rank order */
+int nq_allgather_sketches(nq_comm* c, const nq_params* p, const int32_t* d_local, uint64_t n_local, int32_t* d_all);
+int nq_bcast_sketches(nq_comm* c, const nq_params* p, int32_t* d_sketches, uint64_t n, int root);
+/* per-shard results of the same query batch -> one result, each query sorted (count, gid) descending */
+int nq_hits_merge(const nq_hits* const* parts, int nparts, nq_hits** out);
+int nq_hits_from_arrays(const uint64_t* ptr, const uint32_t* counts, const uint32_t* gids, uint64_t nq, nq_hits** out);
 
 /* ---- synthetic inputs, generated directly in HBM for the benchmarks ------ */
 int nq_synth_genomes_device(nq_ctx* ctx, uint64_t seed, uint64_t first_genome, uint64_t n,

@@ -6,7 +6,8 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libniqki_b200.so")
+# NIQKI_B200_LIB: another build of the same library (the measurement build of `make tuning`)
+LIB_PATH = os.environ.get("NIQKI_B200_LIB") or os.path.join(HERE, "lib", "libniqki_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
 NQ_OK, NQ_ERR_INVALID, NQ_ERR_CUDA, NQ_ERR_UNSUPPORTED, NQ_ERR_OVERFLOW = range(5)
@@ -57,6 +58,18 @@ SYMBOLS = {
     "nq_device_copy": (C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_int]),
     "nq_sketch_batch_device": (C.c_int, [_VP, _P, _VP, C.c_uint64, _VP, C.c_uint64, _VP, _VP]),
     "nq_densify_device": (C.c_int, [_VP, _P, _VP, C.c_uint64, _VP]),
+    "nq_index_sketches_device": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP]),
+    "nq_matrix_tile": (C.c_int, [_VP, _VP, C.c_uint32, C.c_int, _VP]),
+    "nq_comm_unique_id": (C.c_int, [_VP]),
+    "nq_comm_init_rank": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.POINTER(_VP)]),
+    "nq_comm_init_all": (C.c_int, [C.POINTER(_VP), C.c_int, C.POINTER(_VP)]),
+    "nq_comm_destroy": (C.c_int, [_VP]),
+    "nq_comm_info": (C.c_int, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nq_shard_range": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "nq_allgather_sketches": (C.c_int, [_VP, _P, _VP, C.c_uint64, _VP]),
+    "nq_bcast_sketches": (C.c_int, [_VP, _P, _VP, C.c_uint64, C.c_int]),
+    "nq_hits_merge": (C.c_int, [C.POINTER(_VP), C.c_int, C.POINTER(_VP)]),
+    "nq_hits_from_arrays": (C.c_int, [_VP, _VP, _VP, C.c_uint64, C.POINTER(_VP)]),
     "nq_index_build": (C.c_int, [_VP, _P, _VP, C.c_uint64, C.c_uint32, C.POINTER(_VP)]),
     "nq_index_build_device": (C.c_int, [_VP, _P, _VP, C.c_uint64, C.c_uint32, C.POINTER(_VP)]),
     "nq_index_free": (C.c_int, [_VP]),

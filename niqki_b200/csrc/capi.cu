@@ -422,3 +422,15 @@ extern "C" int nq_matrix_rows(nq_index* ix, uint32_t row_begin, uint32_t row_end
   NQ_CUDA(cudaSetDevice(ix->ctx->device));
   return nq_matrix_impl(ix, row_begin, row_end, wrap16, counts);
 }
+
+extern "C" int nq_index_sketches_device(nq_index* ix, uint32_t row_begin, uint32_t row_end, int32_t* d_sketches) {
+  if (!ix) return nq_set_error(NQ_ERR_INVALID, "null index");
+  NQ_CUDA(cudaSetDevice(ix->ctx->device));
+  return nq_index_sketches_impl(ix, row_begin, row_end, d_sketches);
+}
+
+extern "C" int nq_matrix_tile(nq_index* ix, const int32_t* d_row_sketches, uint32_t nrows, int wrap16, uint32_t* counts) {
+  if (!ix) return nq_set_error(NQ_ERR_INVALID, "null index");
+  NQ_CUDA(cudaSetDevice(ix->ctx->device));
+  return nq_matrix_tile_impl(ix, d_row_sketches, nrows, wrap16, counts);
+}

@@ -521,7 +521,7 @@ __global__ void split16_dir_kernel(const uint2* __restrict__ dir, const uint32_t
 using namespace nq;
 
 int nq_index_make_split16(nq_index* ix) {
-  static const char* env = getenv("NQ_SPLIT16");  // "0": keep the u32 gather (measurement only)
+  static const char* env = nq_tuning_env("NQ_SPLIT16");  // "0": keep the u32 gather (measurement only)
   // below 65600 genomes the dummy ids of the query kernel (just above n) would not be >= 2^16
   if (ix->elem != 4 || ix->n < 65600u || ix->n > 131072u || ix->p.S > 15 || (env && env[0] == '0')) return NQ_OK;
   nq_ctx* ctx = ix->ctx;
@@ -672,7 +672,8 @@ int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketch
   nq_dfree(ctx, d_fpT);
   nq_dfree(ctx, d_total);
   d_fpT = nullptr; d_total = nullptr;
-  if ((st = nq_index_make_split16(ix)) != NQ_OK || (st = nq_query_prepare(ix)) != NQ_OK) return fail(st);
+  if ((st = nq_index_make_split16(ix)) != NQ_OK || (st = nq_slab_build(ix)) != NQ_OK || (st = nq_query_prepare(ix)) != NQ_OK)
+    return fail(st);
   *out = ix;
   return NQ_OK;
 }
@@ -686,6 +687,7 @@ extern "C" int nq_index_free(nq_index* ix) {
     nq_dfree(ix->ctx, ix->d_dir3);
     nq_dfree(ix->ctx, ix->d_gids16);
     nq_dfree(ix->ctx, ix->d_pool);
+    nq_slab_free(ix);
   }
   delete ix;
   return NQ_OK;
@@ -699,7 +701,8 @@ extern "C" int nq_index_info(const nq_index* ix, uint64_t* n_postings, uint32_t*
   if (gid_base) *gid_base = ix->gid_base;
   if (device_bytes)
     *device_bytes = (uint64_t)ix->p.F * (2ull * ix->row_stride + ix->gid_stride) * ix->elem +
-                    (ix->d_dir3 ? (uint64_t)ix->p.F * (16ull * ix->row_stride + 2ull * ix->gid_stride) : 0);
+                    (ix->d_dir3 ? (uint64_t)ix->p.F * (16ull * ix->row_stride + 2ull * ix->gid_stride) : 0) +
+                    (ix->slab_G ? ix->slab_granules * ix->slab_G * 2 + (uint64_t)ix->p.F * (ix->p.range / 32) * 16 : 0);
   return NQ_OK;
 }
 
@@ -784,6 +787,7 @@ static int import_t(nq_index* ix, const uint32_t* list_sizes, const uint32_t* gi
       (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
     return nq_set_error(NQ_ERR_CUDA, "index import failed: %s", cudaGetErrorString(e));
   NQ_TRY(nq_index_make_split16(ix));
+  NQ_TRY(nq_slab_build(ix));
   return nq_query_prepare(ix);
 }
 

@@ -5,6 +5,8 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "niqki_b200.h"
@@ -34,7 +36,7 @@ struct nq_ctx {
   uint64_t last_query_gathered = 0;  // gids gathered by the last query call (roofline numerator)
 };
 
-enum NqKernelKind { NQK_SCAN = 0, NQK_DENSIFY = 1, NQK_TRANSPOSE = 2, NQK_CELLSORT = 3, NQK_QUERY = 4, NQK_MATRIX = 5 };
+enum NqKernelKind { NQK_SCAN = 0, NQK_DENSIFY = 1, NQK_TRANSPOSE = 2, NQK_CELLSORT = 3, NQK_QUERY = 4, NQK_MATRIX = 5, NQK_SLAB = 6 };
 
 // RAII bracket: records an event pair around a kernel launch when timing is on
 struct NqTimer {
@@ -80,6 +82,17 @@ inline void nq_dfree(nq_ctx* ctx, void* p) {
 
 int nq_params_check(const nq_params* p);
 
+// Measurement knobs (NQ_* environment variables) exist only in builds with -DNQ_TUNING; the
+// product library never lets the environment choose a kernel.
+inline const char* nq_tuning_env(const char* name) {
+#ifdef NQ_TUNING
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+
 // ---- sketch.cu
 int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint64_t bases_capacity,
                      const uint64_t* h_offsets, uint64_t n, const uint32_t* h_rec_entry, uint64_t n_entries,
@@ -106,6 +119,17 @@ struct nq_index {
   // {begin, mid, end, 0} with mid = first posting >= 65536.  Halves the bytes the query kernel gathers.
   uint4* d_dir3 = nullptr;       // [F][row_stride]
   uint16_t* d_gids16 = nullptr;  // [F][gid_stride] + kQuerySlack
+  // slab side structure (compact shards, 2^W >= 32; slab.cu): the query kernel's own copy of the
+  // postings.  A list occupies 1..3 granules of G ids (16 B * G/8, granule-aligned, padded with ids
+  // >= n that land in spare counter words); meta[cell][fp/32] = {b0, b1, b2, base} gives the list of
+  // fp its granule count (bit fp%32 of b0 + 2*b1) and its first granule (base + weighted popcount of
+  // the bits below); b2 marks lists longer than 3 granules, whose tail stays in d_gids behind a
+  // descriptor granule.  A probe is one 16-byte meta read + one or two sectors of ids.
+  uint4* d_meta = nullptr;        // [F][range/32]
+  uint2* d_slab = nullptr;        // granules, 8-byte units; granule 0 is the all-padding dummy
+  uint32_t* d_cell_gran = nullptr;  // [F+1] first granule of each cell
+  uint32_t slab_G = 0;            // ids per granule (8, 16, 32, 64); 0 = no slab
+  uint64_t slab_granules = 0;
   // device-resident results of the last nq_query_batch_device(out == NULL)
   uint64_t* d_pool = nullptr;
   uint64_t pool_cap = 0;
@@ -121,7 +145,11 @@ int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketch
 constexpr uint32_t kMaxCompact = 65400;  // genomes per shard in the u16 form (leaves room for the query kernel's dummy ids)
 constexpr uint32_t kQuerySlack = 64;     // elements reserved behind d_gids[F][gid_stride]
 int nq_query_prepare(nq_index* ix);      // fills that slack; call once the index arrays exist
+int nq_slab_build(nq_index* ix);            // slab.cu: builds the slab side structure when the shard calls for it
+void nq_slab_free(nq_index* ix);
 int nq_index_make_split16(nq_index* ix);  // index.cu: builds d_dir3 / d_gids16 when the shard size calls for them
 int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t min_score, nq_hits** out);
 int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t wrap_mask, uint32_t* d_out);
 int nq_matrix_impl(nq_index* ix, uint32_t row_begin, uint32_t row_end, int wrap16, uint32_t* h_counts);
+int nq_index_sketches_impl(nq_index* ix, uint32_t row_begin, uint32_t row_end, int32_t* d_sketches);
+int nq_matrix_tile_impl(nq_index* ix, const int32_t* d_rows, uint32_t nrows, int wrap16, uint32_t* h_counts);

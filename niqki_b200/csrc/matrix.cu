@@ -81,13 +81,68 @@ __global__ void __launch_bounds__(256) extract_rows_kernel(const void* __restric
 
 using namespace nq;
 
+// sketches of local genomes [rb, re) rebuilt from the posting lists: d_sk[(g-rb)*F + cell] = fp or -1
+static int extract_rows(nq_index* ix, uint32_t rb, uint32_t re, int32_t* d_sk) {
+  nq_ctx* ctx = ix->ctx;
+  const uint32_t F = ix->p.F, range = (uint32_t)ix->p.range, rows = re - rb;
+  const bool staged = (size_t)range * 4 <= 64 * 1024;
+  const size_t smem = staged ? (size_t)range * 4 : 0;
+  if (smem > 48 * 1024)
+    NQ_CUDA(ix->elem == 2 ? cudaFuncSetAttribute(extract_rows_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : cudaFuncSetAttribute(extract_rows_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NQ_CUDA(cudaMemsetAsync(d_sk, 0xFF, (size_t)rows * F * 4, ctx->stream));
+  NqTimer timer(ctx, NQK_MATRIX);
+  const unsigned grid = (unsigned)std::min<uint64_t>(F, (uint64_t)ctx->sm_count * 16);
+#define NQ_EXTRACT(IT, ST)                                                                                          \
+  extract_rows_kernel<IT, ST><<<grid, 256, smem, ctx->stream>>>(ix->d_row, static_cast<const IT*>(ix->d_gids), F, range, \
+                                                                ix->row_stride, ix->gid_stride, rb, re, d_sk)
+  if (ix->elem == 2) { if (staged) NQ_EXTRACT(uint16_t, true); else NQ_EXTRACT(uint16_t, false); }
+  else { if (staged) NQ_EXTRACT(uint32_t, true); else NQ_EXTRACT(uint32_t, false); }
+#undef NQ_EXTRACT
+  NQ_CHECK_LAUNCH(ctx);
+  return NQ_OK;
+}
+
+int nq_index_sketches_impl(nq_index* ix, uint32_t row_begin, uint32_t row_end, int32_t* d_sketches) {
+  if (!ix || (row_begin < row_end && !d_sketches)) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  if (row_begin > row_end || row_end > ix->n)
+    return nq_set_error(NQ_ERR_INVALID, "row range [%u,%u) outside [0,%u)", row_begin, row_end, ix->n);
+  if (row_begin == row_end) return NQ_OK;
+  return extract_rows(ix, row_begin, row_end, d_sketches);
+}
+
+// counts[r*n + j] = cells in which row sketch r and local genome j carry the same valid fingerprint
+// (a dense query): one tile of the genome x genome grid, rows from anywhere, columns = this shard.
+int nq_matrix_tile_impl(nq_index* ix, const int32_t* d_rows, uint32_t nrows, int wrap16, uint32_t* h_counts) {
+  if (!ix || (nrows && (!d_rows || !h_counts))) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  if (nrows == 0) return NQ_OK;
+  nq_ctx* ctx = ix->ctx;
+  const uint32_t n = ix->n, F = ix->p.F;
+  const uint32_t per_pass = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nrows, (2ull << 30) / ((uint64_t)n * 4)));
+  uint32_t* d_counts = nullptr;
+  NQ_TRY(nq_dmalloc(ctx, (void**)&d_counts, (size_t)per_pass * n * 4));
+  int st = NQ_OK;
+  cudaError_t e = cudaSuccess;
+  for (uint32_t r0 = 0; r0 < nrows && st == NQ_OK; r0 += per_pass) {
+    const uint32_t rows = std::min(per_pass, nrows - r0);
+    st = nq_query_dense_impl(ix, d_rows + (size_t)r0 * F, rows, wrap16 ? 0xFFFFu : 0xFFFFFFFFu, d_counts);
+    if (st != NQ_OK) break;
+    if ((e = cudaMemcpyAsync(h_counts + (size_t)r0 * n, d_counts, (size_t)rows * n * 4, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
+      break;
+  }
+  nq_dfree(ctx, d_counts);
+  if (e != cudaSuccess) return nq_set_error(NQ_ERR_CUDA, "matrix tile failed: %s", cudaGetErrorString(e));
+  return st;
+}
+
 int nq_matrix_impl(nq_index* ix, uint32_t row_begin, uint32_t row_end, int wrap16, uint32_t* h_counts) {
   if (!ix || !h_counts) return nq_set_error(NQ_ERR_INVALID, "null argument");
   if (row_begin > row_end || row_end > ix->n)
     return nq_set_error(NQ_ERR_INVALID, "row range [%u,%u) outside [0,%u)", row_begin, row_end, ix->n);
   if (row_begin == row_end) return NQ_OK;
   nq_ctx* ctx = ix->ctx;
-  const uint32_t n = ix->n, F = ix->p.F, range = (uint32_t)ix->p.range;
+  const uint32_t n = ix->n, F = ix->p.F;
   // rows per pass: rebuilt sketches + dense counts of one pass within ~6 GB of scratch
   const uint64_t per_row = ((uint64_t)F + n) * 4;
   const uint32_t rows_per_pass =
@@ -98,33 +153,12 @@ int nq_matrix_impl(nq_index* ix, uint32_t row_begin, uint32_t row_end, int wrap1
   int st = nq_dmalloc(ctx, (void**)&d_counts, (size_t)rows_per_pass * n * 4);
   if (st != NQ_OK) { nq_dfree(ctx, d_sk); return st; }
   const uint32_t wrap_mask = wrap16 ? 0xFFFFu : 0xFFFFFFFFu;
-  const bool staged = (size_t)range * 4 <= 64 * 1024;
-  const size_t smem = staged ? (size_t)range * 4 : 0;
   cudaError_t e = cudaSuccess;
-  if (smem > 48 * 1024)
-    e = ix->elem == 2 ? cudaFuncSetAttribute(extract_rows_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                      : cudaFuncSetAttribute(extract_rows_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    nq_dfree(ctx, d_sk); nq_dfree(ctx, d_counts);
-    return nq_set_error(NQ_ERR_CUDA, "matrix rows: %s", cudaGetErrorString(e));
-  }
   for (uint32_t rb = row_begin; rb < row_end && st == NQ_OK; rb += rows_per_pass) {
     const uint32_t re = std::min(row_end, rb + rows_per_pass);
     const uint32_t rows = re - rb;
     // local ids of the block (postings hold gid - gid_base; matrix rows are local to the shard too)
-    if ((e = cudaMemsetAsync(d_sk, 0xFF, (size_t)rows * F * 4, ctx->stream)) != cudaSuccess) break;
-    {
-      NqTimer timer(ctx, NQK_MATRIX);
-      const unsigned grid = (unsigned)std::min<uint64_t>(F, (uint64_t)ctx->sm_count * 16);
-#define NQ_EXTRACT(IT, ST)                                                                                          \
-  extract_rows_kernel<IT, ST><<<grid, 256, smem, ctx->stream>>>(ix->d_row, static_cast<const IT*>(ix->d_gids), F, range, \
-                                                                ix->row_stride, ix->gid_stride, rb, re, d_sk)
-      if (ix->elem == 2) { if (staged) NQ_EXTRACT(uint16_t, true); else NQ_EXTRACT(uint16_t, false); }
-      else { if (staged) NQ_EXTRACT(uint32_t, true); else NQ_EXTRACT(uint32_t, false); }
-#undef NQ_EXTRACT
-      ctx->launches++;
-      if ((e = cudaPeekAtLastError()) != cudaSuccess) break;
-    }
+    if ((st = extract_rows(ix, rb, re, d_sk)) != NQ_OK) break;
     st = nq_query_dense_impl(ix, d_sk, rows, wrap_mask, d_counts);
     if (st != NQ_OK) break;
     if ((e = cudaMemcpyAsync(h_counts + (size_t)(rb - row_begin) * n, d_counts, (size_t)rows * n * 4, cudaMemcpyDeviceToHost,

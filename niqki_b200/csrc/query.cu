@@ -29,35 +29,10 @@
 #include <type_traits>
 #include <vector>
 
-#include "device_common.cuh"
-#include "internal.h"
+#include "query_common.cuh"
 
 namespace nq {
 
-struct QueryArgs {
-  const int32_t* qsk;  // [nq][F]
-  const void* dir;     // [F][row_stride] packed {begin,end} (u16 pair in a u32, or uint2)
-  const void* gids;    // [F][gid_stride] local ids (u16 or u32)
-  uint32_t F, range, n, row_stride, gid_stride, gid_base, min_score, wrap_mask;
-  uint64_t* pool;  // count<<32 | gid
-  uint64_t pool_cap;
-  unsigned long long* cursor;  // [0] pool cursor, [1] posting entries gathered (statistics)
-  uint64_t* hit_begin;  // [nq]
-  uint32_t* hit_n;      // [nq]
-  uint32_t* gcounts;    // global counters [gridDim.x][n] (GLOBAL mode only)
-  uint32_t* slice_hits;           // GLOBAL mode finish scratch: [queries per launch][slices]
-  unsigned long long* slice_base;
-  uint32_t slices;
-  uint32_t parts;       // GLOBAL mode, segment-table form: gridDim.y CTAs share one query (counters zeroed before, finished after)
-  uint32_t prefetch;    // cooperative L2 prefetch of upcoming cells (only when a few chunks of cells fit in L2)
-  const uint4* dir3;       // split16 side arrays of the index (internal.h), or null
-  const uint16_t* gids16;
-  uint64_t nq_total;    // queries of the whole call (CTA size of the small-shard form)
-  uint64_t q_end;       // one past the last query of the launch (kDual16: a CTA's second query may not exist)
-  uint32_t* dense;      // when set: row q of [nq][n] takes every genome's count instead of the thresholded hit list (--matrix)
-};
-
-enum CountMode { kPack16 = 0, kSmem32 = 1, kGlobal32 = 2, kDual16 = 3 };
 
 // id carried by stream slots past the end of a group's stream: lands in spare counter word `lane`
 // (shared-memory modes) or is skipped (global mode).  Must fit IT: n <= kMaxCompact in the u16 form.
@@ -113,21 +88,6 @@ struct DirWord3 {
   __device__ __forceinline__ uint32_t end() const { return z; }
 };
 
-// clamped shift: PTX shl.b32 yields 0 for shift amounts >= 32 (C++ leaves that undefined)
-__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t s) {
-  uint32_t r;
-  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
-  return r;
-}
-// `if (s < total) red.shared.add(addr, v)` as ONE predicated instruction (no branch, no reconvergence)
-__device__ __forceinline__ void red_shared_add_if_lt(uint32_t saddr, uint32_t v, uint32_t s, uint32_t total) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %2, %3;\n\t@q red.shared.add.u32 [%0], %1;\n\t}"
-               :: "r"(saddr), "r"(v), "r"(s), "r"(total) : "memory");
-}
-// Pull a contiguous region into L2 through the bulk-copy engine (no LSU/L1TEX work, no registers).
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
-}
 
 // The co-resident query CTAs sweep the cells roughly in step, so each one pulls ITS slice of the
 // directory rows and posting arrays of a chunk of cells two chunks ahead of where it is: DRAM then
@@ -164,79 +124,6 @@ __device__ __forceinline__ void prefetch_chunk(const QueryArgs& a, const PfSlice
   if (p.len[1]) l2_prefetch_bulk(static_cast<const char*>(a.gids) + (size_t)chunk * p.pitch[1] + p.off[1], p.len[1]);
 }
 
-// ---- threshold (:661-665) + compaction, shared by both gather forms: count the hits, reserve a pool
-// segment with one atomicAdd, then write (count, gid) in gid order
-template <int MODE, int NT>
-__device__ __forceinline__ void query_finish(const QueryArgs& a, uint64_t q, const uint32_t* cnt, uint32_t gathered,
-                                             uint32_t shift) {
-  __shared__ uint32_t s_warp[NT / 32];
-  __shared__ unsigned long long s_base;
-  __shared__ uint32_t s_total;
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr unsigned kFull = 0xFFFFFFFFu;
-  auto count_of = [&](uint32_t g) -> uint32_t {
-    uint32_t c;
-    if (MODE == kPack16) c = (cnt[g >> 1] >> ((g & 1) * 16)) & 0xFFFFu;
-    else if (MODE == kDual16) c = (cnt[g] >> shift) & 0xFFFFu;
-    else if (MODE == kGlobal32) c = __ldcg(&cnt[g]);
-    else c = cnt[g];
-    return c & a.wrap_mask;
-  };
-
-  if (a.dense) {  // all-vs-all rows (:570-598): the whole counter array, coalesced
-    uint32_t* row = a.dense + q * a.n;
-    for (uint32_t g = tid; g < a.n; g += NT) row[g] = count_of(g);
-    return;
-  }
-  uint32_t mine = 0;
-  for (uint32_t g = tid; g < a.n; g += NT) mine += count_of(g) >= a.min_score;
-#pragma unroll
-  for (int d = 16; d; d >>= 1) {
-    mine += __shfl_xor_sync(kFull, mine, d);
-    gathered += __shfl_xor_sync(kFull, gathered, d);
-  }
-  if (lane == 0) {
-    s_warp[warp] = mine;
-    if (gathered) atomicAdd(a.cursor + 1, (unsigned long long)gathered);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t t = 0;
-    for (int w = 0; w < NT / 32; ++w) t += s_warp[w];
-    s_total = t;
-    s_base = atomicAdd(a.cursor, (unsigned long long)t);
-    a.hit_begin[q] = s_base;
-    a.hit_n[q] = t;
-  }
-  __syncthreads();
-  const uint32_t total = s_total;
-  const unsigned long long base = s_base;
-  if (total == 0 || base + total > a.pool_cap) return;  // overflow: host re-runs with a larger pool
-
-  uint32_t done = 0;
-  for (uint32_t g0 = 0; g0 < a.n; g0 += NT) {
-    const uint32_t g = g0 + tid;
-    uint32_t c = 0;
-    bool hit = false;
-    if (g < a.n) {
-      c = count_of(g);
-      hit = c >= a.min_score;
-    }
-    if (__syncthreads_count(hit) == 0) continue;  // hits are sparse: most chunks of NT genomes hold none
-    const unsigned bal = __ballot_sync(kFull, hit);
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t before = 0, chunk = 0;
-    for (int w = 0; w < NT / 32; ++w) {
-      const uint32_t x = s_warp[w];
-      before += w < (int)warp ? x : 0;
-      chunk += x;
-    }
-    if (hit) a.pool[base + done + before + __popc(bal & ((1u << lane) - 1))] = ((uint64_t)c << 32) | (a.gid_base + g);
-    done += chunk;
-    __syncthreads();  // s_warp is rewritten by the next chunk that holds a hit
-  }
-}
 
 // IDX = uint32_t when every posting index F*gid_stride fits 32 bits (always for S <= 15 in the compact form)
 template <typename IT, int MODE, int NT, typename IDX, int R = 4, int D = 2>
@@ -799,7 +686,7 @@ static bool query_dual_ok(const nq_index* ix) {
   return ix->p.S <= 15 && ix->elem == 2 && (size_t)ix->n * 4 + 128 <= 54 * 1024 && ix->n + 64 < 65536;
 }
 static int query_form(const nq_index* ix, bool small) {
-  static const char* env = getenv("NQ_QUERY_FORM");
+  static const char* env = nq_tuning_env("NQ_QUERY_FORM");
   const bool seg_ok = (uint64_t)ix->p.F * ix->row_stride < (1ull << 32);  // 32-bit directory indexes
   if (env && seg_ok) {
     if (!strcmp(env, "stream")) return kFormStream;
@@ -837,7 +724,7 @@ static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, un
   // queries vs 16k / 20k / 25k / 35k genomes: 12.9 / ~14 / 15.5 / 18.3 ms as one 1024-thread CTA per SM ->
   // 8.1 / 10.5 / 13.3 / 16.6 ms.  Sized WITHOUT regard for L1 (256 threads up to 51 KB, 512 up to 100 KB) the
   // same kernels were slower than the 1024-thread form (16.6 vs 15.4 ms at 25k, 21.6 vs 17.2 ms at 50k).
-  static const char* mid_env = getenv("NQ_QUERY_MID");  // "0": the 1024-thread forms (measurement only)
+  static const char* mid_env = nq_tuning_env("NQ_QUERY_MID");  // "0": the 1024-thread forms (measurement only)
   const bool mid_on = !(mid_env && mid_env[0] == '0');
   const bool mid256 = mid_on && !small && 4 * (smem + 1024 + 4400) + 40 * 1024 <= 228 * 1024;
   const bool mid512 = mid_on && !small && !mid256 && 2 * (smem + 1024 + 12600) + 48 * 1024 <= 228 * 1024;
@@ -846,7 +733,7 @@ static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, un
   // then 256-thread CTAs (4 queries per SM, 8 warps each: the same 32 warps on half the shared memory).
   // 12.5k genomes x 10k queries: 11.8 -> 6.65 ms; 10k x 10k: 6.63 -> 5.94 ms; but 10k x 2k: 1.29 -> 1.40 ms and
   // 10k x 1k: 0.64 -> 0.70 ms (half-empty waves), which stay on 128 threads.  NQ_QUERY_NT overrides.
-  static const char* nt_env = getenv("NQ_QUERY_NT");
+  static const char* nt_env = nq_tuning_env("NQ_QUERY_NT");
   const size_t cta128 = smem + 1024 + 800;  // dynamic + per-CTA reserve + static tables
   const size_t occ128 = std::min<size_t>(8, (228 * 1024) / cta128);
   const bool l1_starved = 228 * 1024 - occ128 * cta128 < 24 * 1024;
@@ -870,18 +757,25 @@ static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, un
   NQ_SEG_DISPATCH(kSmem32)
 #undef NQ_SEG_DISPATCH
 }
+// slab.cu
+bool nq_slab_layout(const nq_index* ix, int& mode, size_t& smem);
+cudaError_t nq_slab_launch(const nq_index* ix, int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0,
+                           cudaStream_t st, int* occ);
+
 static cudaError_t launch_query(const nq_index* ix, int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0,
                                 cudaStream_t st, int* occ = nullptr) {
+  if (a.slab) return nq_slab_launch(ix, mode, smem, nb, a, q0, st, occ);
   return ix->elem == 2 ? launch_query_it<uint16_t>(ix, mode, smem, nb, a, q0, st, occ)
                        : launch_query_it<uint32_t>(ix, mode, smem, nb, a, q0, st, occ);
 }
 
 // Chunks of lead of the cooperative L2 prefetch (0 = off): the window of lead + 1 chunks of kPfCells cells
 // (directory rows + posting arrays) must sit in L2.  NQ_QUERY_PF_AHEAD overrides the lead (measurement only).
-static uint32_t query_prefetch_lead(const nq_index* ix) {
-  static const char* env = getenv("NQ_QUERY_PF_AHEAD");
+static uint32_t query_prefetch_lead(const nq_index* ix, bool slab) {
+  static const char* env = nq_tuning_env("NQ_QUERY_PF_AHEAD");
   const uint32_t lead = env ? (uint32_t)atoi(env) : kPfAhead;
-  const uint64_t chunk = (uint64_t)kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem;
+  const uint64_t chunk = slab ? (uint64_t)kPfCells * (ix->p.range / 32) * 16 + ix->slab_granules * ix->slab_G * 2 / ix->p.F * kPfCells
+                              : (uint64_t)kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem;
   return (lead + 1) * chunk <= (64ull << 20) ? lead : 0u;
 }
 
@@ -897,11 +791,11 @@ static uint64_t query_wave(const nq_index* ix, int mode, size_t smem, const Quer
   // atomics run ~6x faster there than in HBM: 193 vs 33 G/s measured); the grid is filled by cutting
   // every query over `parts` CTAs instead (set_query_parts)
   if (mode == kGlobal32) return std::max<uint64_t>(1, std::min<uint64_t>(nq, (64ull << 20) / ((uint64_t)ix->n * 4)));
-  static const char* env = getenv("NQ_QUERY_WAVES");  // "0": one grid (measurement only)
+  static const char* env = nq_tuning_env("NQ_QUERY_WAVES");  // "0": one grid (measurement only)
   if (!a.prefetch || (env && env[0] == '0')) return nq;
   int occ = 0;
   if (launch_query(ix, mode, smem, 1, a, 0, nullptr, &occ) != cudaSuccess || occ <= 0) return nq;
-  static const char* cap_env = getenv("NQ_QUERY_WAVE_SM");  // cap of resident queries per SM in a wave (measurement only)
+  static const char* cap_env = nq_tuning_env("NQ_QUERY_WAVE_SM");  // cap of resident queries per SM in a wave (measurement only)
   if (cap_env && atoi(cap_env) > 0) occ = std::min(occ, atoi(cap_env));
   const uint64_t slots = (uint64_t)occ * ix->ctx->sm_count;
   if (nq <= slots) return nq;
@@ -981,9 +875,15 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
 
   int mode;
   size_t smem;
-  query_layout(ix, mode, smem);
+  const bool slab = ix->slab_G && nq_slab_layout(ix, mode, smem);  // granule form of the postings (slab.cu)
+  if (slab) {
+    a.meta = ix->d_meta; a.slab = ix->d_slab; a.cell_gran = ix->d_cell_gran; a.mgroups = a.range / 32;
+  } else {
+    query_layout(ix, mode, smem);
+  }
   // the prefetch window (kPfAhead + 1 chunks of kPfCells cells: directory rows + posting arrays) must sit in L2
-  a.prefetch = query_prefetch_lead(ix);
+  a.prefetch = query_prefetch_lead(ix, slab);
+  if (const char* ex = nq_tuning_env("NQ_QUERY_EXP")) a.exp = (uint32_t)atoi(ex);
 
   const uint64_t q_per_launch = query_wave(ix, mode, smem, a, nq);
   if (set_query_parts(ix, mode, q_per_launch, a) != NQ_OK) { nq_dfree(ctx, a.slice_hits); delete hits; return NQ_ERR_CUDA; }
@@ -1093,8 +993,14 @@ int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, ui
   a.dense = d_out;
   int mode;
   size_t smem;
-  query_layout(ix, mode, smem);
-  a.prefetch = query_prefetch_lead(ix);
+  const bool slab = ix->slab_G && nq_slab_layout(ix, mode, smem);
+  if (slab) {
+    a.meta = ix->d_meta; a.slab = ix->d_slab; a.cell_gran = ix->d_cell_gran; a.mgroups = a.range / 32;
+  } else {
+    query_layout(ix, mode, smem);
+  }
+  a.prefetch = query_prefetch_lead(ix, slab);
+  if (const char* ex = nq_tuning_env("NQ_QUERY_EXP")) a.exp = (uint32_t)atoi(ex);
   const uint64_t q_per_launch = query_wave(ix, mode, smem, a, nq);
   if (set_query_parts(ix, mode, q_per_launch, a) != NQ_OK) { nq_dfree(ctx, a.slice_hits); return NQ_ERR_CUDA; }
   unsigned long long* d_cursor = nullptr;  // [1] = gather statistics

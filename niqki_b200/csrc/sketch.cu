@@ -536,9 +536,9 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
   }
   // short entries, small sketches (lines mode): warp-per-entry fused kernel, no global sketch traffic
   if (!h_rec_entry && longest + p->K <= 4096 && P.S <= 11 && P.K <= 32) {
-    static const char* env = getenv("NQ_READS_KERNEL");  // "0": the CTA-per-entry kernels (measurement only)
+    static const char* env = nq_tuning_env("NQ_READS_KERNEL");  // "0": the CTA-per-entry kernels (measurement only)
     if (!(env && env[0] == '0')) {
-      static const char* dens_env = getenv("NQ_READS_DENSIFY");  // "cell": the all-cells densification (measurement only)
+      static const char* dens_env = nq_tuning_env("NQ_READS_DENSIFY");  // "cell": the all-cells densification (measurement only)
       const bool listed = !(dens_env && dens_env[0] == 'c');
       uint64_t* d_offsets = nullptr;
       NQ_TRY(nq_dmalloc(ctx, (void**)&d_offsets, (n + 1) * sizeof(uint64_t)));
@@ -603,7 +603,7 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
   } else {
     // the sketch stays in HBM/L2; a coarse filter (8 or 4 bits per cell) takes the shared memory instead
     DevParams PG = P;
-    static const char* env = getenv("NQ_SCAN_FILTER");  // "0": no filter (measurement only)
+    static const char* env = nq_tuning_env("NQ_SCAN_FILTER");  // "0": no filter (measurement only)
     const size_t room = ctx->smem_optin - 2048 - 1024;
     if (!small && !(env && env[0] == '0')) {
       if (P.W >= 8 && (size_t)P.F <= room) PG.filter = 8;

@@ -54,7 +54,7 @@ class Context:
     def launches(self) -> int:
         return int(self.L.nq_ctx_launch_count(self.h))
 
-    KINDS = ("scan", "densify", "transpose", "cell_sort", "query", "matrix")
+    KINDS = ("scan", "densify", "transpose", "cell_sort", "query", "matrix", "slab")
 
     def set_timing(self, on: bool = True):
         check(self.L.nq_ctx_set_timing(self.h, int(on)))

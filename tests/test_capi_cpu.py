@@ -73,3 +73,51 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in txt.replace("SURVEY", "").lower() or f in ("synth.cu", "__init__.py"), f
+
+
+def test_shard_range_and_hits_merge_host_side(capi):
+    """nq_shard_range / nq_hits_from_arrays / nq_hits_merge are host code: contiguous gid blocks and
+    the merge of per-shard hit lists == one sort by (count, gid) descending (niqki_index.cpp:685)."""
+    L = capi.lib()
+    for n, R in [(100_000, 8), (10, 3), (7, 8), (0, 2)]:
+        covered = []
+        for r in range(R):
+            b, e = C.c_uint64(), C.c_uint64()
+            capi.check(L.nq_shard_range(n, R, r, C.byref(b), C.byref(e)))
+            assert b.value <= e.value <= n
+            covered += list(range(b.value, e.value)) if n <= 100 else [(b.value, e.value)]
+        if n <= 100:
+            assert covered == list(range(n))
+        else:
+            assert covered[0][0] == 0 and covered[-1][1] == n and all(covered[i][1] == covered[i + 1][0] for i in range(R - 1))
+    rng = np.random.default_rng(3)
+    nq, shards = 17, 3
+    parts, allhits = [], [[] for _ in range(nq)]
+    handles = (C.c_void_p * shards)()
+    for s in range(shards):
+        ptr, cnt, gid = [0], [], []
+        for q in range(nq):
+            k = int(rng.integers(0, 6))
+            gs = rng.choice(np.arange(s * 1000, (s + 1) * 1000), size=k, replace=False)
+            cs = rng.integers(1, 5, size=k)
+            order = np.lexsort((gs, cs))[::-1]
+            for i in order:
+                cnt.append(int(cs[i])); gid.append(int(gs[i])); allhits[q].append((int(cs[i]), int(gs[i])))
+            ptr.append(len(cnt))
+        p = np.array(ptr, np.uint64); c = np.array(cnt + [0], np.uint32); g = np.array(gid + [0], np.uint32)
+        h = C.c_void_p()
+        capi.check(L.nq_hits_from_arrays(p.ctypes.data, c.ctypes.data, g.ctypes.data, nq, C.byref(h)))
+        handles[s] = h
+    out = C.c_void_p()
+    capi.check(L.nq_hits_merge(handles, shards, C.byref(out)))
+    total = int(L.nq_hits_total(out))
+    mp = np.ctypeslib.as_array(L.nq_hits_ptr(out), shape=(nq + 1,))
+    mc = np.ctypeslib.as_array(L.nq_hits_counts(out), shape=(max(total, 1),))
+    mg = np.ctypeslib.as_array(L.nq_hits_gids(out), shape=(max(total, 1),))
+    for q in range(nq):
+        exp = sorted(allhits[q], reverse=True)
+        got = list(zip(mc[mp[q]:mp[q + 1]].tolist(), mg[mp[q]:mp[q + 1]].tolist()))
+        assert got == exp
+    for s in range(shards):
+        L.nq_hits_free(handles[s])
+    L.nq_hits_free(out)

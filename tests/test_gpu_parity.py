@@ -531,3 +531,86 @@ def test_full_size_properties(nb, ctx):
     m = g.query_matrix()
     assert np.array_equal(np.diag(m), np.full(n, 32768, np.uint32)) and np.array_equal(m, m.T)
     assert 5 <= np.median(m[~np.eye(n, dtype=bool)]) <= 45  # background collisions ~22
+
+
+# ---- kernel forms of the headline configurations at realistic list statistics --------------------
+def _fp_cdf(lam=152.6, W=12, H=4):
+    """Distribution of a sketch cell of a random genome: min over ~Poisson(lam) k-mers of the W-bit
+    fingerprint (HLL part on top of W-H low hash bits) — what the posting lists of configs[1]/[2]
+    look like without sketching 50 Gbases in a test."""
+    M = W - H
+    top = (1 << H) - 1
+    pm = np.zeros(1 << W)
+    for h in range(top + 1):
+        ph = 2.0 ** -(top + 1 - h) if h > 0 else 2.0 ** -top
+        pm[h << M:(h + 1) << M] = ph / (1 << M)
+    cdf = np.cumsum(pm)
+    surv = np.exp(-lam * np.concatenate([[0.0], cdf]))
+    p = surv[:-1] - surv[1:]
+    return np.cumsum(p / p.sum())
+
+
+def _realistic_sketches(rng, n, F, cdf):
+    table = np.minimum(np.searchsorted(cdf, (np.arange(65536) + 0.5) / 65536.0, side="right"), len(cdf) - 1).astype(np.int32)
+    out = np.empty((n, F), np.int32)
+    for r0 in range(0, n, 4096):
+        r1 = min(n, r0 + 4096)
+        out[r0:r1] = table[rng.integers(0, 65536, size=(r1 - r0, F), dtype=np.uint16)]
+    return out
+
+
+def _queries_like(rng, sks, nq, cdf):
+    """Mutated copies (10 %, 40 %, 90 % of the cells redrawn) of random genomes + unrelated sketches."""
+    n, F = sks.shape
+    q = _realistic_sketches(rng, nq, F, cdf)
+    for i in range(nq - 4):
+        keep = rng.random(F) >= (0.1, 0.4, 0.9)[i % 3]
+        parent = sks[rng.integers(0, n)]
+        q[i, keep] = parent[keep]
+    q[-1, ::7] = -1       # empty cells and out-of-range fingerprints are not probed (:655)
+    q[-2, ::5] = 1 << 20
+    return q
+
+
+@pytest.mark.parametrize("n,S,J,what", [
+    (10_000, 13, 0.1, "slab G=8, 128-thread CTAs (configs[1] shard)"),
+    (12_500, 12, 0.1, "slab G=8, 256-thread CTAs (configs[2] shard)"),
+    (25_000, 11, 0.1, "slab G=16 (100k index on 4 GPUs)"),
+    (50_000, 10, 0.1, "slab G=32/64 (100k index on 2 GPUs)"),
+    (65_400, 10, 0.0, "largest u16 shard, every genome reported"),
+    (72_000, 10, 0.1, "split16 segment-table form, 1024 threads (100k index on 1 GPU)"),
+    (140_000, 9, 0.1, "u32 ids beyond split16"),
+])
+def test_query_forms_at_realistic_list_lengths(nb, ctx, n, S, J, what):
+    """Postings and hit lists of >= 32 queries against the oracle, at the shard sizes of the headline
+    configurations and with their list-length statistics (many groups of 32 cells per warp)."""
+    rng = np.random.default_rng(n + S)
+    ps = dict(K=31, S=S, W=12, H=4)
+    F = 1 << S
+    cdf = _fp_cdf()
+    o = oracle(J=J, **ps)
+    g = gpu_index(nb, ctx, J=J, **ps)
+    sks = _realistic_sketches(rng, n, F, cdf)
+    sks[1::997] = sks[0]                      # a cluster of identical genomes: lists longer than three granules
+    sks[rng.random((n, F)) < 0.002] = -1
+    g.insert_sketches(sks)
+    o.insert_sketches(sks)
+    rp, ogids = o.csr()
+    sizes, gids = g.export_postings()
+    assert np.array_equal(sizes, np.diff(rp).astype(np.uint32)), what
+    assert np.array_equal(gids, ogids), what
+    q = _queries_like(rng, sks, 40, cdf)
+    ptr, c, gid = g.query_sketches(q)
+    ohp, oc, og = o.query_batch(q)
+    assert np.array_equal(ptr, ohp) and np.array_equal(c, oc) and np.array_equal(gid, og), what
+    assert ptr[-1] >= 24, "the mutated copies must report hits"
+    # device-sketch entry point, many queries (more than one resident wave for the small forms)
+    import torch
+    reps = 64 if n <= 25_000 else 8
+    dq = torch.from_numpy(np.tile(q, (reps, 1))).cuda()
+    ptr2, c2, gid2 = g.query_sketches(dq)
+    ctx.sync()
+    for r in (0, reps // 2, reps - 1):
+        lo, hi = ptr2[r * 40], ptr2[(r + 1) * 40]
+        assert np.array_equal(ptr2[r * 40:(r + 1) * 40 + 1] - lo, ohp), what
+        assert np.array_equal(c2[lo:hi], oc) and np.array_equal(gid2[lo:hi], og), what
