@@ -33,7 +33,7 @@ GENOME_LEN = 5_000_000
 K, S, W, H, J = 31, 15, 12, 4, 0.1
 RATES = (0.001, 0.01, 0.05)
 OPS_PER_BASE = 38  # algorithmic int32 ops per base of the sketch scan
-METRIC = "Gbases/s sketched (index 10k x 5 Mbp genomes + query 1k mutated copies, per GPU shard)"
+METRIC = "Gbases/s sketched (configs[1] per GPU: index 10k x 5 Mbp genomes + query 1k mutated copies); query sketches/s vs 100k-genome index in query_100k"
 
 
 def parse():
@@ -42,10 +42,14 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--genomes", type=int, default=0, help="genomes per GPU (default: 10000; 12500 at 8 GPUs)")
+    ap.add_argument("--genomes", type=int, default=0, help="genomes per GPU (default: 10000 = configs[1], at every N)")
     ap.add_argument("--queries", type=int, default=0, help="queries per GPU (default: genomes/10)")
     ap.add_argument("--genome-len", type=int, default=GENOME_LEN)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-q100k", action="store_true", help="skip the query_100k section of the contract line")
+    ap.add_argument("--no-q100k-auto", action="store_true", help="N > 1: skip the replicated-layout timing of query_100k")
+    ap.add_argument("--q100k-genomes", type=int, default=100_000)
+    ap.add_argument("--q100k-queries", type=int, default=10_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-genomes", type=int, default=0, help="genomes per GPU in the e2e leg (default: all that fit host RAM)")
     ap.add_argument("--reads", type=int, default=0, help="c4: reads per GPU (default 10M)")
@@ -599,22 +603,32 @@ def run_c5(args):
         dist.destroy_process_group()
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
-    if args.workload == "q100k":
-        return run_q100k(args)
-    if args.workload == "c4":
-        return run_c4(args)
-    if args.workload == "c5":
-        return run_c5(args)
+def _brute_force_hits(torch, sk_shard, gid_base, sk_q, F, min_score, range_):
+    """Independent check of the query path (torch eager, no library code): per-genome counts of equal
+    valid fingerprints of `sk_q` rows against this rank's shard sketches, thresholded like :661-665."""
+    out = []
+    n = sk_shard.shape[0]
+    for qi in range(sk_q.shape[0]):
+        q = sk_q[qi]
+        valid = (q >= 0) & (q < range_)
+        cnt = torch.zeros(n, dtype=torch.int64, device=sk_shard.device)
+        for g0 in range(0, n, 2048):
+            blk = sk_shard[g0:g0 + 2048]
+            cnt[g0:g0 + 2048] = ((blk == q[None, :]) & valid[None, :]).sum(1)
+        hit = torch.nonzero(cnt >= max(min_score, 0)).flatten()
+        out.append(sorted(((int(cnt[g]), gid_base + int(g)) for g in hit.tolist()), reverse=True))
+    return out
 
+
+def run_contract(args):
+    """The contract line: configs[1] per GPU (weak scaling) + the BASELINE metric's second half in the
+    same JSON line: query sketches/s against a 100k-genome index sharded over the N GPUs."""
     import torch
     import torch.distributed as dist
 
     import niqki_b200
     from niqki_b200.capi import check, lib
+    from niqki_b200.shard import Comm, merge_hits, torch_bcast_bytes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -623,47 +637,21 @@ def main():
         args.gpus = world
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    gloo = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)   # barriers + max-over-ranks of the timings
+        gloo = dist.new_group(backend="gloo")             # per-rank hit lists travel to rank 0 on the host
 
-    G = args.genomes or (12500 if world == 8 else 10000)
+    G = args.genomes or 10000          # configs[1] per GPU at every N
     Q = args.queries or max(1, G // 10)
     L = args.genome_len
-    Lp = (L + 15) // 16 * 16  # entries start 16-byte aligned in HBM
     Lc = lib()
     stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream shared by torch and the library
     torch.cuda.set_stream(stream)
     ctx = niqki_b200.Context(local, stream)
     ix = niqki_b200.Index(S=S, K=K, W=W, H=H, min_fract=J, ctx=ctx)
     F = ix.F
-
-    # ---- synthetic inputs, generated in HBM (untimed)
-    g0 = rank * G
-    q0 = rank * Q
-    d_idx = torch.empty(G * L + 64, dtype=torch.uint8, device=dev)
-    check(Lc.nq_synth_genomes_device(ctx.h, SEED, g0, G, L, C.c_void_p(d_idx.data_ptr())))
-    qid = np.arange(q0, q0 + Q, dtype=np.uint64)
-    parents = (qid % np.uint64(G * world)).astype(np.uint64)  # queries are copies of genomes 0..Q*world-1
-    thr = thresholds([RATES[int(q) % 3] for q in qid])
-    d_qry = torch.empty(Q * L + 64, dtype=torch.uint8, device=dev)
-    check(Lc.nq_synth_mutants_device(ctx.h, SEED, parents.ctypes.data, qid.ctypes.data, thr.ctypes.data, Q, L,
-                                     C.c_void_p(d_qry.data_ptr())))
-    idx_offs = np.arange(G + 1, dtype=np.uint64) * L
-    qry_offs = np.arange(Q + 1, dtype=np.uint64) * L
-    sk_idx = torch.empty((G, F), dtype=torch.int32, device=dev)
-    sk_qry = torch.empty((Q, F), dtype=torch.int32, device=dev)
-    sk_all = torch.empty((Q * world, F), dtype=torch.int32, device=dev) if world > 1 else sk_qry
-    fl_idx = torch.empty(G, dtype=torch.int32, device=dev)
-    fl_qry = torch.empty(Q, dtype=torch.int32, device=dev)
-    torch.cuda.synchronize()
-
-    def step_device():
-        ix.compute_sketches(d_idx, idx_offs, out=sk_idx, flags=fl_idx)
-        ix.insert_sketches(sk_idx, gid_base=g0)
-        ix.compute_sketches(d_qry, qry_offs, out=sk_qry, flags=fl_qry)
-        if world > 1:
-            dist.all_gather_into_tensor(sk_all, sk_qry)
-        ix.query_sketches(sk_all, fetch=False)
+    comm = Comm(ctx, rank, world, torch_bcast_bytes(dist, dev)) if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -684,6 +672,43 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def gather_merge(part):
+        """Per-shard (ptr, counts, gids) -> merged lists on rank 0 (nq_hits_merge); None elsewhere."""
+        if world == 1:
+            return part
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(part, parts, dst=0, group=gloo)
+        return merge_hits(parts) if rank == 0 else None
+
+    # ---- synthetic inputs, generated in HBM (untimed)
+    g0, q0 = rank * G, rank * Q
+    d_idx = torch.empty(G * L + 64, dtype=torch.uint8, device=dev)
+    check(Lc.nq_synth_genomes_device(ctx.h, SEED, g0, G, L, C.c_void_p(d_idx.data_ptr())))
+    qid = np.arange(q0, q0 + Q, dtype=np.uint64)
+    parents = (qid % np.uint64(G * world)).astype(np.uint64)  # queries are copies of genomes 0..Q*world-1
+    thr = thresholds([RATES[int(q) % 3] for q in qid])
+    d_qry = torch.empty(Q * L + 64, dtype=torch.uint8, device=dev)
+    check(Lc.nq_synth_mutants_device(ctx.h, SEED, parents.ctypes.data, qid.ctypes.data, thr.ctypes.data, Q, L,
+                                     C.c_void_p(d_qry.data_ptr())))
+    idx_offs = np.arange(G + 1, dtype=np.uint64) * L
+    qry_offs = np.arange(Q + 1, dtype=np.uint64) * L
+    sk_idx = torch.empty((G, F), dtype=torch.int32, device=dev)
+    sk_qry = torch.empty((Q, F), dtype=torch.int32, device=dev)
+    sk_all = torch.empty((Q * world, F), dtype=torch.int32, device=dev) if world > 1 else sk_qry
+    fl_idx = torch.empty(G, dtype=torch.int32, device=dev)
+    fl_qry = torch.empty(Q, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    last = {}
+
+    def step_device():
+        ix.compute_sketches(d_idx, idx_offs, out=sk_idx, flags=fl_idx)
+        ix.insert_sketches(sk_idx, gid_base=g0)
+        ix.compute_sketches(d_qry, qry_offs, out=sk_qry, flags=fl_qry)
+        if world > 1:
+            comm.allgather_sketches(ix.p, sk_qry, sk_all)       # nq_allgather_sketches: NCCL, u16 on the wire
+        part = ix.query_sketches(sk_all)                          # hit lists on the host, sorted (:685)
+        last["hits"] = gather_merge(part)                         # nq_hits_merge of the shards' lists on rank 0
+
     for _ in range(args.warmup):
         step_device()
     ctx.set_timing(True)
@@ -702,43 +727,61 @@ def main():
     value = bases_per_step * args.steps / (ms_total / 1e3) / 1e9
     info = ix.info()
 
-    # ---- correctness spot check (untimed): parents are found, counts match the device sketches
-    ptr, cnt, gid = ix.query_sketches(sk_all[: min(8, Q)])
-    first_hits = [int(gid[int(ptr[i])]) if ptr[i + 1] > ptr[i] else -1 for i in range(min(8, Q))]
+    # ---- parity of the merged result: the first queries against a brute-force count over the shards'
+    # sketches (torch eager, every rank its own shard, merged on rank 0 by a plain sort)
+    ncheck = min(64 if world > 1 else 16, Q * world)
+    bf = _brute_force_hits(torch, sk_idx, g0, sk_all[:ncheck], F, ix.min_score, int(ix.p.range))
+    if world > 1:
+        allbf = [None] * world if rank == 0 else None
+        dist.gather_object(bf, allbf, dst=0, group=gloo)
+    else:
+        allbf = [bf]
+    parity_ok = None
+    first_hits = None
+    if rank == 0:
+        ptr, cnt, gid = last["hits"]
+        parity_ok = True
+        for qi in range(ncheck):
+            exp = sorted((h for r in allbf for h in r[qi]), reverse=True)
+            got = list(zip(cnt[int(ptr[qi]):int(ptr[qi + 1])].tolist(), gid[int(ptr[qi]):int(ptr[qi + 1])].tolist()))
+            parity_ok = parity_ok and got == exp
+        first_hits = [int(gid[int(ptr[i])]) if ptr[i + 1] > ptr[i] else -1 for i in range(min(8, Q))]
 
-    # ---- e2e: the same job through the host-buffer C ABI (H2D of the sequences, D2H of sketches
-    # for the index call and of the sorted hit lists), on as many genomes as the host can pin
+    # ---- e2e: the same job through the host-buffer C ABI: pinned host sequences in (packed to 2 bits
+    # per base by the library on the way, K1), sketches stay in HBM, query sketches exchanged over NCCL,
+    # sorted hit lists out and merged on rank 0 — every step.
     e2e = None
     if not args.no_e2e:
-        # every rank of the node pins its own copy: split what the host has left between them
         avail = mem_available_bytes() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
         Ge = args.e2e_genomes or G
-        need = (Ge + Q) * L + (Ge + Q) * F * 4
-        while Ge > 64 and avail and need * 1.5 > avail:
+        while Ge > 64 and avail and (Ge + Q) * L * 1.6 > avail:
             Ge //= 2
-            need = (Ge + Q) * L + (Ge + Q) * F * 4
         Qe = max(1, min(Q, Ge // 10))
         h_idx = torch.empty(Ge * L, dtype=torch.uint8, pin_memory=True)
         h_qry = torch.empty(Qe * L, dtype=torch.uint8, pin_memory=True)
         h_idx.copy_(d_idx[: Ge * L]); h_qry.copy_(d_qry[: Qe * L])
-        h_sk_idx = torch.empty((Ge, F), dtype=torch.int32, pin_memory=True)
-        h_sk_qry = torch.empty((Qe, F), dtype=torch.int32, pin_memory=True)
         torch.cuda.synchronize()
         n_idx_b, n_qry_b = h_idx.numpy(), h_qry.numpy()
-        n_sk_idx, n_sk_qry = h_sk_idx.numpy(), h_sk_qry.numpy()
         eo_idx = np.arange(Ge + 1, dtype=np.uint64) * L
         eo_qry = np.arange(Qe + 1, dtype=np.uint64) * L
+        e_sk_idx, e_sk_qry = sk_idx[:Ge], sk_qry[:Qe]
+        e_sk_all = torch.empty((Qe * world, F), dtype=torch.int32, device=dev) if world > 1 else e_sk_qry
+        h_flags = np.zeros(max(Ge, Qe), np.uint32)
         d2h = [0]
 
         def step_e2e():
-            ix.compute_sketches(n_idx_b, eo_idx, out=n_sk_idx)      # H2D bases, D2H sketches
-            ix.insert_sketches(n_sk_idx, gid_base=g0)               # H2D sketches
-            ix.compute_sketches(n_qry_b, eo_qry, out=n_sk_qry)
-            p_, c_, g_ = ix.query_sketches(n_sk_qry)                # H2D sketches, D2H sorted hits
-            d2h[0] = n_sk_idx.nbytes + n_sk_qry.nbytes + c_.nbytes + g_.nbytes + p_.nbytes
+            ix.sketch_records_to_device(n_idx_b, eo_idx, e_sk_idx, h_flags)      # H2D (packed), sketches stay on the device
+            ix.insert_sketches(e_sk_idx, gid_base=g0)
+            ix.sketch_records_to_device(n_qry_b, eo_qry, e_sk_qry, h_flags)
+            if world > 1:
+                comm.allgather_sketches(ix.p, e_sk_qry, e_sk_all)
+            part = ix.query_sketches(e_sk_all)                                    # D2H sorted hits
+            d2h[0] = sum(int(x.nbytes) for x in part) + 4 * (Ge + Qe)
+            last["e2e_hits"] = gather_merge(part)
 
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e()
+        h2d0 = ctx.h2d_bytes
         barrier()
         t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, 3))
@@ -750,17 +793,21 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e_bases = (Ge + Qe) * L * world
         e2e = {"value": e2e_bases * e2e_steps / float(dt.item()) / 1e9, "unit": "Gbases/s",
-               "h2d_bytes_per_step": int((Ge + Qe) * L + (Ge + Qe) * F * 4), "d2h_bytes_per_step": int(d2h[0]),
-               "genomes": Ge, "queries": Qe, "steps": e2e_steps,
-               "note": "nq_sketch_batch / nq_index_build / nq_query_batch with pinned host buffers; no inter-rank exchange in this leg"}
-        del h_idx, h_qry, h_sk_idx, h_sk_qry
+               "h2d_bytes_per_step": int((ctx.h2d_bytes - h2d0) // e2e_steps), "d2h_bytes_per_step": int(d2h[0]),
+               "host_bytes_read_per_step": int((Ge + Qe) * L), "genomes": Ge, "queries": Qe, "steps": e2e_steps,
+               "note": "nq_sketch_records (host characters packed to 2 bits/base by the library, K1) / nq_index_build_device / "
+                       "nq_allgather_sketches / nq_query_batch_device + nq_hits_merge; h2d = bytes that crossed PCIe"}
+        del h_idx, h_qry
+    del d_idx, d_qry, sk_idx, sk_qry, sk_all
+    ix.close_index()
+    torch.cuda.empty_cache()
+
+    q100k = None
+    if not args.no_q100k:
+        q100k = q100k_section(args, torch, dist, niqki_b200, ctx, comm, gloo, world, rank, local, dev, stream, barrier, gather_merge)
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except (OSError, ValueError):
-            pass
+        peaks = _peaks()
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
         scan_ms, scan_n = kt["scan"]
@@ -772,61 +819,44 @@ def main():
         q_bytes = 4 * gathered + nq_total * F * (8 + 2)  # gids + row pairs + u16 sketch (+ 8 B/hit, negligible)
         q_gbs = q_bytes / (q_ms / max(q_n, 1) / 1e3) / 1e9 if q_ms else None
         sm_clk = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-        int_peak = 148 * 128 * sm_clk * 1e6 / 1e12  # Tint32-op/s: 148 SMs x 128 lanes x sampled SM clock
-        traffic = {}
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        except (OSError, ValueError):
-            pass
-
-        def ncu_traffic(kernel, scale=1.0):
-            t = traffic.get(kernel)
-            ok = t and t.get("genomes_per_gpu") == G and t.get("queries") == nq_total
-            return int(t["dram_bytes_per_launch"] * scale) if ok else None
-
+        int_peak, int_src = _int_peak(peaks, sm_clk)
         b_ms, b_n = kt["cell_sort"]
-        t_ms, t_n = kt["transpose"]
-        # index build, minimal bytes per posting: u16 fingerprint in, u16 gid out, + the directory
+        s_ms, s_n = kt["slab"]
         elem = 2 if G <= 65400 else 4
         b_bytes = info["n_postings"] * 2 * elem + F * (1 << W) * 2 * elem
         b_gbs = b_bytes / (b_ms / max(b_n, 1) / 1e3) / 1e9 if b_ms else None
-
         line = {
             "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"configs[{2 if world == 8 else 1}]: {G} synthetic {L} bp genomes --index + {Q} mutated "
-                                   f"copies --query per GPU, x{world} GPUs",
+            "config": {"workload": f"configs[1] on every GPU: {G} synthetic {L} bp genomes --index + {Q} mutated copies --query per GPU, "
+                                   f"x{world} GPUs (index sharded by genome id; query sketches all-gathered, hits merged on rank 0)",
                        "K": K, "S": S, "W": W, "H": H, "minjac": J, "genomes_per_gpu": G, "queries_per_gpu": Q,
-                       "l2": "inputs larger than L2 (>= 50 GB of sequence per step)", "parallelism": f"shard-by-gid x{world}"},
+                       "l2": "inputs larger than L2 (>= 50 GB of sequence per step)", "parallelism": f"shard-by-gid x{world}",
+                       "collective": "nq_allgather_sketches (NCCL, u16 on the wire)" if world > 1 else "none"},
             "query_sketches_per_s": nq_total / (q_ms / max(q_n, 1) / 1e3) if q_ms else None,
             "index_postings": info["n_postings"],
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt.items()},
-            # dominant kernel (>90% of the step): integer-ALU bound, DESIGN.md 4 / SURVEY 8d
             "roofline": {"kernel": "sketch_scan_kernel", "bound": "int32-alu",
                          "achieved": scan_gbases * OPS_PER_BASE / 1e3 if scan_gbases else None, "peak": int_peak,
                          "unit": "Tint32-op/s", "frac": (scan_gbases * OPS_PER_BASE / 1e3 / int_peak) if scan_gbases else None,
-                         # ncu captured the index launch (G entries); scaled to the average launch of this run
-                         "traffic": ncu_traffic("sketch_scan_kernel", bases_per_scan / (G * L)),
+                         "traffic": _ncu_traffic("sketch_scan_kernel", G, nq_total, bases_per_scan / (G * L)),
                          "algorithmic_ops_per_base": OPS_PER_BASE, "gbases_per_s": scan_gbases,
-                         "launches": int(scan_n), "ms_per_launch": scan_ms / max(scan_n, 1),
-                         "peak_source": "148 SMs x 128 int32 lanes x SM clock sampled during the run (no measured INT32 "
-                                        "figure in MEASURED_PEAKS.json; SURVEY 8d fallback)",
+                         "launches": int(scan_n), "ms_per_launch": scan_ms / max(scan_n, 1), "peak_source": int_src,
                          "hbm": {"achieved": scan_gbases, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": scan_gbases / hbm_peak if scan_gbases else None,
                                  "note": "1 B/base algorithmic: this kernel is not HBM-bound"}},
-            # the HBM-bound kernel of the path (north_star target >= 0.5)
-            "roofline_query": {"kernel": "query_count_seg_kernel (seg8 form)" if os.environ.get("NQ_QUERY_FORM", "seg8") == "seg8"
-                               else "query_count_kernel", "bound": "hbm", "achieved": q_gbs, "peak": hbm_peak,
+            "roofline_query": {"kernel": "slab_resolve_kernel + query_slab_kernel", "bound": "hbm", "achieved": q_gbs, "peak": hbm_peak,
                                "unit": "GB/s", "frac": (q_gbs / hbm_peak) if q_gbs else None,
-                               "traffic": ncu_traffic("query_count_seg_kernel" if os.environ.get("NQ_QUERY_FORM", "seg8") == "seg8"
-                                                      else "query_count_kernel"), "peak_source": peak_src,
+                               "traffic": _ncu_traffic("query_slab_kernel", G, nq_total), "peak_source": peak_src,
                                "algorithmic_bytes": q_bytes, "gathered_postings": gathered,
                                "launches": int(q_n), "ms_per_launch": q_ms / max(q_n, 1)},
             "roofline_build": {"kernel": "cell_build_kernel", "bound": "hbm", "achieved": b_gbs, "peak": hbm_peak, "unit": "GB/s",
-                               "frac": (b_gbs / hbm_peak) if b_gbs else None, "traffic": ncu_traffic("cell_build_kernel"),
+                               "frac": (b_gbs / hbm_peak) if b_gbs else None, "traffic": _ncu_traffic("cell_build_kernel", G, nq_total),
                                "algorithmic_bytes": b_bytes, "launches": int(b_n), "ms_per_launch": b_ms / max(b_n, 1),
-                               "note": "instruction-issue bound (59% issue-active, shared-memory atomics): profiles/r01_ncu_cb5.txt"},
+                               "slab_ms_per_build": s_ms / max(args.steps, 1)},
+            "query_100k": q100k,
+            "parity_ok": parity_ok, "parity_checked_queries": ncheck,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "first_hits": first_hits,
         }
         if not args.no_cpu_baseline and world == 1:
@@ -838,6 +868,173 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def q100k_section(args, torch, dist, niqki_b200, ctx, comm, gloo, world, rank, local, dev, stream, barrier, gather_merge):
+    """BASELINE metric, second half: query sketches/s of 10k mutated-copy queries (minjac 0.1) against a
+    100k-genome index sharded by genome id over the N GPUs (strong scaling: total work fixed).  A step =
+    all-gather of the query sketches (each rank holds 1/N of them) + counting on every shard + sorted hit
+    lists to the host + merge on rank 0 — all inside the timed region.  When N > 1 the same queries are
+    also timed in the layout the library would pick when the whole index fits one GPU's HBM (every GPU
+    holds all shards, queries are split, no exchange)."""
+    from niqki_b200.capi import check, lib
+    from niqki_b200.shard import merge_hits
+
+    Lc = lib()
+    Gt, Qt, L = args.q100k_genomes, args.q100k_queries, args.genome_len
+    G, Q = Gt // world, Qt // world
+    ix = niqki_b200.Index(S=S, K=K, W=W, H=H, min_fract=J, ctx=ctx)
+    F = ix.F
+    g0, q0 = rank * G, rank * Q
+    B = 2500
+    buf = torch.empty(B * L + 64, dtype=torch.uint8, device=dev)
+    sk_idx = torch.empty((G, F), dtype=torch.int32, device=dev)
+    sk_qry = torch.empty((Q, F), dtype=torch.int32, device=dev)
+    t_build = time.perf_counter()
+    for b0 in range(0, G, B):
+        nb = min(B, G - b0)
+        check(Lc.nq_synth_genomes_device(ctx.h, SEED, g0 + b0, nb, L, C.c_void_p(buf.data_ptr())))
+        ix.compute_sketches(buf, np.arange(nb + 1, dtype=np.uint64) * L, out=sk_idx[b0:b0 + nb])
+    ix.insert_sketches(sk_idx, gid_base=g0)
+    for b0 in range(0, Q, B):
+        nb = min(B, Q - b0)
+        qid = np.arange(q0 + b0, q0 + b0 + nb, dtype=np.uint64)
+        parents = (qid % np.uint64(Gt)).astype(np.uint64)
+        thr = thresholds([RATES[int(q) % 3] for q in qid])
+        check(Lc.nq_synth_mutants_device(ctx.h, SEED, parents.ctypes.data, qid.ctypes.data, thr.ctypes.data, nb, L,
+                                         C.c_void_p(buf.data_ptr())))
+        ix.compute_sketches(buf, np.arange(nb + 1, dtype=np.uint64) * L, out=sk_qry[b0:b0 + nb])
+    del buf
+    sk_all = torch.empty((Q * world, F), dtype=torch.int32, device=dev) if world > 1 else sk_qry
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+    last = {}
+
+    def step():
+        if world > 1:
+            comm.allgather_sketches(ix.p, sk_qry, sk_all)
+        last["hits"] = gather_merge(ix.query_sketches(sk_all))
+
+    def timed_wall(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        step()
+    ctx.set_timing(True)
+    ctx.timing_reset()
+    ms_total = timed_wall(step, steps)
+    q_ms, q_n = ctx.timing()["query"]
+    gathered = ctx.last_query_gathered
+    ctx.set_timing(False)
+    info = ix.info()
+
+    # parity of the merged lists: first queries against a brute-force count over the shards' sketches
+    ncheck = min(64, Q * world)
+    bf = _brute_force_hits(torch, sk_idx, g0, sk_all[:ncheck], F, ix.min_score, int(ix.p.range))
+    if world > 1:
+        allbf = [None] * world if rank == 0 else None
+        dist.gather_object(bf, allbf, dst=0, group=gloo)
+    else:
+        allbf = [bf]
+    parity_ok = None
+    if rank == 0:
+        ptr, cnt, gid = last["hits"]
+        parity_ok = True
+        for qi in range(ncheck):
+            exp = sorted((h for r in allbf for h in r[qi]), reverse=True)
+            got = list(zip(cnt[int(ptr[qi]):int(ptr[qi + 1])].tolist(), gid[int(ptr[qi]):int(ptr[qi + 1])].tolist()))
+            parity_ok = parity_ok and got == exp
+
+    # the layout the library picks when every shard fits one GPU: all shards on every GPU, queries split
+    auto = None
+    if world > 1 and not args.no_q100k_auto:
+        shards = [ix]
+        all_idx = torch.empty((Gt, F), dtype=torch.int32, device=dev)
+        comm.allgather_sketches(ix.p, sk_idx, all_idx)
+        full = niqki_b200.Index(S=S, K=K, W=W, H=H, min_fract=J, ctx=ctx)
+        ix.close_index()
+        full.insert_sketches(all_idx, gid_base=0)
+        del all_idx
+
+        def step_auto():
+            last["auto"] = full.query_sketches(sk_qry)   # this rank's queries against the whole index: final lists
+
+        for _ in range(2):
+            step_auto()
+        ms_auto = timed_wall(step_auto, steps)
+        auto = {"layout": f"whole index on each of the {world} GPUs (fits HBM: {full.info()['device_bytes'] / 1e9:.1f} GB), queries split {world} ways, no exchange",
+                "value": Qt * steps / (ms_auto / 1e3), "unit": "query sketches/s", "ms_per_step": ms_auto / steps}
+        full.close()
+        del shards
+    del sk_idx
+    out = None
+    if rank == 0:
+        peaks = _peaks()
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        q_bytes = 4 * gathered + Qt * F * (8 + 2)  # this rank's launch: all queries against its shard
+        q_gbs = q_bytes / (q_ms / max(q_n, 1) / 1e3) / 1e9 if q_ms else None
+        out = {"metric": "query sketches/s vs 100k-genome index (10k mutated-copy queries, minjac 0.1)",
+               "value": Qt * steps / (ms_total / 1e3), "unit": "query sketches/s", "ms_per_step": ms_total / steps, "steps": steps,
+               "scaling": "strong", "layout": f"north star: index sharded by genome id, {G} genomes per GPU x {world}; query sketches "
+                                              f"all-gathered (nq_allgather_sketches), hits merged on rank 0 (nq_hits_merge), inside the timed region",
+               "genomes": Gt, "queries": Qt, "index_postings_per_gpu": info["n_postings"], "index_bytes_per_gpu": info["device_bytes"],
+               "build_wall_s": t_build, "parity_ok": parity_ok, "parity_checked_queries": ncheck,
+               "count_kernel_ms_per_step": q_ms / steps if q_ms else None,
+               "roofline": {"kernel": "query kernels of this shard size (slab form up to 65.4k genomes, split16 segment form above)", "bound": "hbm",
+                            "achieved": q_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": (q_gbs / hbm_peak) if q_gbs else None,
+                            "traffic": _ncu_traffic("query_100k", G, Qt), "algorithmic_bytes": q_bytes, "gathered_postings": gathered,
+                            "launches": int(q_n), "ms_per_launch": q_ms / max(q_n, 1)},
+               "auto_layout": auto}
+    ix.close()
+    return out
+
+
+def _int_peak(peaks, sm_clk):
+    """INT32 roofline denominator: the issue-rate microbenchmark of tools/microbench.cu when its record is
+    committed (profiles/int32_peak.json: measured int32 ops per clock per SM), else lanes x clock."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "int32_peak.json")))
+        per_clk = float(rec["int32_ops_per_clk_per_sm"])
+        return 148 * per_clk * sm_clk * 1e6 / 1e12, f"measured: {per_clk:.1f} int32 ops/clk/SM (tools/microbench.cu, {rec.get('source', 'profiles/int32_peak.json')}) x 148 SMs x SM clock sampled during the run"
+    except (OSError, ValueError, KeyError):
+        return 148 * 128 * sm_clk * 1e6 / 1e12, "148 SMs x 128 int32 lanes x SM clock sampled during the run (no measured INT32 figure available)"
+
+
+def _ncu_traffic(kernel, genomes_per_gpu, queries, scale=1.0):
+    """DRAM bytes per launch from a committed ncu capture of the SAME configuration, else None."""
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except (OSError, ValueError):
+        return None
+    t = traffic.get(kernel)
+    if isinstance(t, list):
+        t = next((x for x in t if x.get("genomes_per_gpu") == genomes_per_gpu and x.get("queries") == queries), None)
+    ok = t and t.get("genomes_per_gpu") == genomes_per_gpu and t.get("queries") == queries
+    return int(t["dram_bytes_per_launch"] * scale) if ok else None
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.workload == "q100k":
+        return run_q100k(args)
+    if args.workload == "c4":
+        return run_c4(args)
+    if args.workload == "c5":
+        return run_c5(args)
+    return run_contract(args)
 
 
 if __name__ == "__main__":

@@ -83,6 +83,8 @@ int nq_ctx_timing_reset(nq_ctx* ctx);
 /* posting-list entries gathered by the most recent query call on this context (its algorithmic
  * HBM traffic is 4 B per entry + 8 B per probed cell + 4 B per sketch cell + 8 B per hit) */
 uint64_t nq_ctx_last_query_gathered(const nq_ctx* ctx);
+/* bytes of sequence (packed or not) that the host-buffer sketch calls have copied to the device so far */
+uint64_t nq_ctx_h2d_bytes(const nq_ctx* ctx);
 /* pinned host memory for fast host<->device copies */
 void* nq_host_alloc(size_t bytes);
 void nq_host_free(void* p);
@@ -91,6 +93,10 @@ void nq_host_free(void* p);
 int nq_device_alloc(nq_ctx* ctx, size_t bytes, void** out);
 int nq_device_free(nq_ctx* ctx, void* p);
 int nq_device_copy(nq_ctx* ctx, void* dst, const void* src, size_t bytes, int kind);
+/* device -> device across two contexts (NVLink peer copy, or through the host where peers are not
+ * enabled); synchronous.  nq_device_fill: stream-ordered memset on the context's stream. */
+int nq_device_copy_peer(nq_ctx* dst_ctx, void* dst, nq_ctx* src_ctx, const void* src, size_t bytes);
+int nq_device_fill(nq_ctx* ctx, void* p, int byte, size_t bytes);
 
 /* ---- sketching: Index::compute_sketch + sketch_densification ---------------------------- */
 /* src/niqki_index.cpp:335-358, 313-331 (and 114-123, 211-236, 240-273, 277-310 underneath).
@@ -111,6 +117,29 @@ int nq_sketch_batch(nq_ctx* ctx, const nq_params* p, const char* bases, const ui
 int nq_sketch_records(nq_ctx* ctx, const nq_params* p, const char* bases, const uint64_t* rec_offsets,
                       uint64_t n_records, const uint32_t* rec_entry, uint64_t n_entries, int32_t* sketches,
                       uint32_t* flags, int sketches_on_device);
+/* K1, sequence packing to 2 bits per base (src/niqki_index.cpp:114-123, 211-221, 255-273 decide the
+ * codes): the host-buffer sketch calls above pack long entries on the host (AVX2, `threads` helper
+ * threads; 0 = all cores, at most 32) so that a base crosses PCIe as 2 bits, plus one bit per base
+ * for the 512-base blocks that hold anything but upper-case ACGT; the device cuts every k-mer out
+ * of the packed stream.  mode: -1 automatic (entries of >= 4096 characters on average), 0 never
+ * (characters travel as they are), 1 always.  Results are identical either way. */
+int nq_ctx_set_host_packing(nq_ctx* ctx, int mode, unsigned threads);
+/* The packer and the packed kernel as entry points of their own (a host that keeps its genomes
+ * packed).  Wire format of a batch of records (rec_offsets[n_records+1] into `bases`):
+ *   codes[words]  u32 per 16 bases, base i at bits 2*(i%16), forward code {A:0,C:1,G:2,T:3}, 0 otherwise;
+ *                 the stream starts with 512 unused bases and ends with 4 zero words;
+ *   blk[blocks]   slot of 512-base block b in `pool`, or 0xFFFFFFFF when all its bytes are upper-case ACGT;
+ *   pool[slots*32] u16 per 16 bases: bit i set = byte i is not upper-case ACGT (both strands' code 0, B3);
+ *   the first K-1 characters of every record are written with the digits of str2numstrand (:255-273).
+ * nq_pack_sizes gives words/blocks for nbytes characters; `pool` needs at most `blocks` slots. */
+int nq_pack_sizes(uint64_t nbytes, uint64_t* words, uint64_t* blocks);
+int nq_pack_sequences(const char* bases, const uint64_t* rec_offsets, uint64_t n_records, uint32_t K, uint32_t* codes,
+                      uint32_t* blk, uint16_t* pool, uint64_t pool_slots, uint64_t* pool_used, unsigned threads);
+/* Index::compute_sketch over a packed batch resident in HBM; offsets[n+1] (host) are the records'
+ * boundaries in the original characters, offsets[0] == 0 */
+int nq_sketch_batch_packed_device(nq_ctx* ctx, const nq_params* p, const uint32_t* d_codes, const uint32_t* d_blk,
+                                  const uint16_t* d_pool, const uint64_t* offsets, uint64_t n, int32_t* d_sketches,
+                                  uint32_t* d_flags);
 /* Same with the characters already in HBM.  `d_bases` must be 16-byte aligned and its allocation
  * must extend to `bases_capacity` >= offsets[n] rounded up to 16.  `offsets` stays a host array.
  * `d_sketches` / `d_flags` are device buffers (d_flags nullable). */

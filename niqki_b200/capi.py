@@ -49,6 +49,7 @@ SYMBOLS = {
     "nq_ctx_timing": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "nq_ctx_timing_reset": (C.c_int, [_VP]),
     "nq_ctx_last_query_gathered": (C.c_uint64, [_VP]),
+    "nq_ctx_h2d_bytes": (C.c_uint64, [_VP]),
     "nq_host_alloc": (_VP, [C.c_size_t]),
     "nq_host_free": (None, [_VP]),
     "nq_sketch_batch": (C.c_int, [_VP, _P, _VP, _VP, C.c_uint64, _VP, _VP]),
@@ -56,6 +57,12 @@ SYMBOLS = {
     "nq_device_alloc": (C.c_int, [_VP, C.c_size_t, C.POINTER(_VP)]),
     "nq_device_free": (C.c_int, [_VP, _VP]),
     "nq_device_copy": (C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_int]),
+    "nq_device_copy_peer": (C.c_int, [_VP, _VP, _VP, _VP, C.c_size_t]),
+    "nq_device_fill": (C.c_int, [_VP, _VP, C.c_int, C.c_size_t]),
+    "nq_ctx_set_host_packing": (C.c_int, [_VP, C.c_int, C.c_uint]),
+    "nq_pack_sizes": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "nq_pack_sequences": (C.c_int, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, _VP, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint]),
+    "nq_sketch_batch_packed_device": (C.c_int, [_VP, _P, _VP, _VP, _VP, _VP, C.c_uint64, _VP, _VP]),
     "nq_sketch_batch_device": (C.c_int, [_VP, _P, _VP, C.c_uint64, _VP, C.c_uint64, _VP, _VP]),
     "nq_densify_device": (C.c_int, [_VP, _P, _VP, C.c_uint64, _VP]),
     "nq_index_sketches_device": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP]),

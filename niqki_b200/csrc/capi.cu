@@ -6,7 +6,10 @@
 #include <cstring>
 #include <vector>
 
+#include <thread>
+
 #include "internal.h"
+#include "pack.h"
 
 static thread_local char g_err[1024] = "";
 
@@ -116,6 +119,7 @@ extern "C" int nq_ctx_create(int device, void* cuda_stream, nq_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
   }
+  if (const char* fg = nq_tuning_env("NQ_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
   // keep freed scratch in the pool instead of returning it to the driver after every call
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -136,6 +140,8 @@ extern "C" int nq_ctx_destroy(nq_ctx* ctx) {
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   for (auto& s : ctx->slot) {
     cudaFree(s.d_bases); cudaFree(s.d_sk); cudaFree(s.d_flags);
+    cudaFree(s.d_codes); cudaFree(s.d_blk); cudaFree(s.d_pool);
+    cudaFreeHost(s.h_codes); cudaFreeHost(s.h_blk); cudaFreeHost(s.h_pool);
     if (s.h2d) cudaEventDestroy(s.h2d);
     if (s.done) cudaEventDestroy(s.done);
     if (s.d2h) cudaEventDestroy(s.d2h);
@@ -184,6 +190,7 @@ extern "C" int nq_ctx_timing_reset(nq_ctx* ctx) {
   return NQ_OK;
 }
 extern "C" uint64_t nq_ctx_last_query_gathered(const nq_ctx* ctx) { return ctx ? ctx->last_query_gathered : 0; }
+extern "C" uint64_t nq_ctx_h2d_bytes(const nq_ctx* ctx) { return ctx ? ctx->h2d_bytes : 0; }
 
 extern "C" void* nq_host_alloc(size_t bytes) {
   void* p = nullptr;
@@ -261,6 +268,12 @@ static int sketch_records_impl(nq_ctx* ctx, const nq_params* p, const char* base
     cap_bases = std::max(cap_bases, offsets[first[cut[b + 1]]] - offsets[first[cut[b]]]);
     cap_entries = std::max(cap_entries, cut[b + 1] - cut[b]);
   }
+  // K1: long entries travel as 2 bits per base (packed on the host by pack.cpp while the previous
+  // batch is on the device); short reads keep the character form (their kernel fuses densification
+  // and the per-record seed fix-up of the packer would dominate)
+  const uint64_t total_bytes = offsets[first[n_entries]] - offsets[first[0]];
+  const bool packed = ctx->pack_mode == 1 || (ctx->pack_mode != 0 && n_rec && total_bytes / n_rec >= 4096);
+  const uint64_t cap_words = nq_pack_words(cap_bases), cap_blocks = nq_pack_blocks(cap_bases);
   cap_bases = (cap_bases + 15 + 16) & ~15ull;
   int st = NQ_OK;
   cudaError_t e = cudaSuccess;
@@ -272,7 +285,18 @@ static int sketch_records_impl(nq_ctx* ctx, const nq_params* p, const char* base
       cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
       cudaEventCreateWithFlags(&s.d2h, cudaEventDisableTiming);
     }
-    if (s.cap_bases < cap_bases) {
+    if (packed && s.cap_words < cap_words) {
+      cudaFree(s.d_codes); cudaFree(s.d_blk); cudaFree(s.d_pool);
+      cudaFreeHost(s.h_codes); cudaFreeHost(s.h_blk); cudaFreeHost(s.h_pool);
+      s.d_codes = s.d_blk = nullptr; s.d_pool = nullptr; s.h_codes = s.h_blk = nullptr; s.h_pool = nullptr; s.cap_words = 0;
+      if ((e = cudaMalloc((void**)&s.d_codes, cap_words * 4)) != cudaSuccess || (e = cudaMalloc((void**)&s.d_blk, cap_blocks * 4)) != cudaSuccess ||
+          (e = cudaMalloc((void**)&s.d_pool, cap_blocks * 64)) != cudaSuccess || (e = cudaMallocHost((void**)&s.h_codes, cap_words * 4)) != cudaSuccess ||
+          (e = cudaMallocHost((void**)&s.h_blk, cap_blocks * 4)) != cudaSuccess || (e = cudaMallocHost((void**)&s.h_pool, cap_blocks * 64)) != cudaSuccess)
+        break;
+      s.dense.resize(cap_words);
+      s.cap_words = cap_words;
+    }
+    if (!packed && s.cap_bases < cap_bases) {
       cudaFree(s.d_bases); s.d_bases = nullptr; s.cap_bases = 0;
       if ((e = cudaMalloc((void**)&s.d_bases, cap_bases)) != cudaSuccess) break;
       s.cap_bases = cap_bases;
@@ -304,13 +328,34 @@ static int sketch_records_impl(nq_ctx* ctx, const nq_params* p, const char* base
       lent.resize(nr);
       for (uint64_t i = 0; i < nr; ++i) lent[i] = rec_entry[r0 + i] - (uint32_t)e0;
     }
-    if (nbytes) e = cudaMemcpyAsync(s.d_bases, bases + base0, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream);
-    if (e != cudaSuccess) { st = nq_set_error(NQ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
-    cudaEventRecord(s.h2d, ctx->copy_stream);
-    cudaStreamWaitEvent(ctx->stream, s.h2d, 0);
     int32_t* d_out = out_on_device ? sketches + e0 * F : s.d_sk;
-    st = nq_launch_sketch(ctx, p, s.d_bases, s.cap_bases, loff.data(), nr, rec_entry ? lent.data() : nullptr, nb, d_out,
-                          s.d_flags);
+    if (packed) {
+      if (b >= (size_t)nslots) cudaEventSynchronize(s.h2d);  // the staging buffers have left for the device
+      unsigned nt = ctx->host_threads ? ctx->host_threads : std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+      const uint64_t words = nq_pack_words(nbytes), blocks = nq_pack_blocks(nbytes);
+      const uint64_t used = nq_pack_host(bases + base0, nbytes, loff.data(), nr, p->K, s.h_codes, s.h_blk, s.h_pool, cap_blocks,
+                                         s.dense.data(), nt);
+      if (used == ~0ull) { st = nq_set_error(NQ_ERR_INVALID, "packer: mask pool overflow"); break; }
+      if ((e = cudaMemcpyAsync(s.d_codes, s.h_codes, words * 4, cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess ||
+          (e = cudaMemcpyAsync(s.d_blk, s.h_blk, blocks * 4, cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess ||
+          (used && (e = cudaMemcpyAsync(s.d_pool, s.h_pool, used * 64, cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess)) {
+        st = nq_set_error(NQ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+        break;
+      }
+      ctx->h2d_bytes += words * 4 + blocks * 4 + used * 64;
+      cudaEventRecord(s.h2d, ctx->copy_stream);
+      cudaStreamWaitEvent(ctx->stream, s.h2d, 0);
+      st = nq_launch_sketch_packed(ctx, p, s.d_codes, s.d_blk, s.d_pool, loff.data(), nr, rec_entry ? lent.data() : nullptr, nb,
+                                   d_out, s.d_flags);
+    } else {
+      if (nbytes) e = cudaMemcpyAsync(s.d_bases, bases + base0, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+      if (e != cudaSuccess) { st = nq_set_error(NQ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
+      ctx->h2d_bytes += nbytes;
+      cudaEventRecord(s.h2d, ctx->copy_stream);
+      cudaStreamWaitEvent(ctx->stream, s.h2d, 0);
+      st = nq_launch_sketch(ctx, p, s.d_bases, s.cap_bases, loff.data(), nr, rec_entry ? lent.data() : nullptr, nb, d_out,
+                            s.d_flags);
+    }
     if (st != NQ_OK) break;
     cudaEventRecord(s.done, ctx->stream);
     cudaStreamWaitEvent(ctx->d2h_stream, s.done, 0);
@@ -433,4 +478,62 @@ extern "C" int nq_matrix_tile(nq_index* ix, const int32_t* d_row_sketches, uint3
   if (!ix) return nq_set_error(NQ_ERR_INVALID, "null index");
   NQ_CUDA(cudaSetDevice(ix->ctx->device));
   return nq_matrix_tile_impl(ix, d_row_sketches, nrows, wrap16, counts);
+}
+
+extern "C" int nq_device_copy_peer(nq_ctx* dst_ctx, void* dst, nq_ctx* src_ctx, const void* src, size_t bytes) {
+  if (!dst_ctx || !src_ctx || (bytes && (!dst || !src))) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  if (bytes == 0) return NQ_OK;
+  NQ_CUDA(cudaSetDevice(src_ctx->device));
+  NQ_CUDA(cudaStreamSynchronize(src_ctx->stream));  // the source is complete
+  NQ_CUDA(cudaSetDevice(dst_ctx->device));
+  NQ_CUDA(cudaMemcpyPeerAsync(dst, dst_ctx->device, src, src_ctx->device, bytes, dst_ctx->stream));
+  NQ_CUDA(cudaStreamSynchronize(dst_ctx->stream));
+  return NQ_OK;
+}
+
+extern "C" int nq_device_fill(nq_ctx* ctx, void* p, int byte, size_t bytes) {
+  if (!ctx || (bytes && !p)) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  NQ_CUDA(cudaSetDevice(ctx->device));
+  NQ_CUDA(cudaMemsetAsync(p, byte, bytes, ctx->stream));
+  return NQ_OK;
+}
+
+// host threads of the packer (0 = hardware concurrency, at most 32) and whether host sequences travel
+// packed: mode -1 auto (entries of >= 4096 characters on average), 0 never, 1 always
+extern "C" int nq_ctx_set_host_packing(nq_ctx* ctx, int mode, unsigned threads) {
+  if (!ctx || mode < -1 || mode > 1) return nq_set_error(NQ_ERR_INVALID, "bad packing mode");
+  ctx->pack_mode = mode;
+  ctx->host_threads = threads;
+  return NQ_OK;
+}
+
+// ---------------------------------------------------------------- K1 as entry points of its own
+extern "C" int nq_pack_sizes(uint64_t nbytes, uint64_t* words, uint64_t* blocks) {
+  if (!words || !blocks) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  *words = nq_pack_words(nbytes);
+  *blocks = nq_pack_blocks(nbytes);
+  return NQ_OK;
+}
+
+extern "C" int nq_pack_sequences(const char* bases, const uint64_t* rec_offsets, uint64_t n_records, uint32_t K, uint32_t* codes,
+                                 uint32_t* blk, uint16_t* pool, uint64_t pool_slots, uint64_t* pool_used, unsigned threads) {
+  if (!rec_offsets || !codes || !blk || (n_records && !bases)) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  if (K < 2 || K > 31) return nq_set_error(NQ_ERR_INVALID, "K=%u outside [2,31]", K);
+  const uint64_t nbytes = rec_offsets[n_records] - rec_offsets[0];
+  std::vector<uint16_t> dense(nq_pack_words(nbytes));
+  if (threads == 0) threads = std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+  const uint64_t used = nq_pack_host(bases + rec_offsets[0], nbytes, rec_offsets, n_records, K, codes, blk, pool, pool ? pool_slots : 0,
+                                     dense.data(), threads);
+  if (used == ~0ull) return nq_set_error(NQ_ERR_OVERFLOW, "mask pool too small (%llu slots)", (unsigned long long)pool_slots);
+  if (pool_used) *pool_used = used;
+  return NQ_OK;
+}
+
+extern "C" int nq_sketch_batch_packed_device(nq_ctx* ctx, const nq_params* p, const uint32_t* d_codes, const uint32_t* d_blk,
+                                             const uint16_t* d_pool, const uint64_t* offsets, uint64_t n, int32_t* d_sketches,
+                                             uint32_t* d_flags) {
+  if (!ctx || !offsets || (n && (!d_codes || !d_blk || !d_sketches))) return nq_set_error(NQ_ERR_INVALID, "null argument");
+  if (n && offsets[0] != 0) return nq_set_error(NQ_ERR_INVALID, "offsets of a packed batch start at 0");
+  NQ_CUDA(cudaSetDevice(ctx->device));
+  return nq_launch_sketch_packed(ctx, p, d_codes, d_blk, d_pool, offsets, n, nullptr, n, d_sketches, d_flags);
 }

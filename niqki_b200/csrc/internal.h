@@ -23,7 +23,14 @@ struct nq_ctx {
     int32_t* d_sk = nullptr; size_t cap_cells = 0;
     uint32_t* d_flags = nullptr; size_t cap_entries = 0;
     cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
+    // 2-bit packed form of the batch (pack.cpp): pinned host staging + device copies
+    uint32_t* h_codes = nullptr; uint32_t* d_codes = nullptr; size_t cap_words = 0;
+    uint32_t* h_blk = nullptr; uint32_t* d_blk = nullptr;
+    uint16_t* h_pool = nullptr; uint16_t* d_pool = nullptr;
+    std::vector<uint16_t> dense;  // host scratch of the packer
   } slot[2];
+  unsigned host_threads = 0;  // packer threads (0 = hardware concurrency, capped)
+  int pack_mode = -1;         // -1 auto (long entries travel packed), 0 never, 1 always
   int sm_count = 148;
   size_t smem_optin = 0;  // max dynamic shared memory per block (opt-in)
   uint64_t launches = 0;  // kernels launched through this context
@@ -34,6 +41,7 @@ struct nq_ctx {
   double kind_ms[8] = {0};
   uint64_t kind_n[8] = {0};
   uint64_t last_query_gathered = 0;  // gids gathered by the last query call (roofline numerator)
+  uint64_t h2d_bytes = 0;            // bytes the host-buffer sketch calls have copied to the device so far
 };
 
 enum NqKernelKind { NQK_SCAN = 0, NQK_DENSIFY = 1, NQK_TRANSPOSE = 2, NQK_CELLSORT = 3, NQK_QUERY = 4, NQK_MATRIX = 5, NQK_SLAB = 6 };
@@ -98,6 +106,10 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
                      const uint64_t* h_offsets, uint64_t n, const uint32_t* h_rec_entry, uint64_t n_entries,
                      int32_t* d_sketches, uint32_t* d_flags);
 int nq_launch_densify(nq_ctx* ctx, const nq_params* p, int32_t* d_sketches, uint64_t n, uint32_t* d_flags);
+// sketch_packed.cu: the same on the 2-bit packed wire format of pack.cpp
+int nq_launch_sketch_packed(nq_ctx* ctx, const nq_params* p, const uint32_t* d_codes, const uint32_t* d_blk, const uint16_t* d_pool,
+                            const uint64_t* h_offsets, uint64_t n, const uint32_t* h_rec_entry, uint64_t n_entries,
+                            int32_t* d_sketches, uint32_t* d_flags);
 
 // ---- index.cu / query.cu / matrix.cu
 struct nq_index {
@@ -129,6 +141,7 @@ struct nq_index {
   uint2* d_slab = nullptr;        // granules, 8-byte units; granule 0 is the all-padding dummy
   uint32_t* d_cell_gran = nullptr;  // [F+1] first granule of each cell
   uint32_t slab_G = 0;            // ids per granule (8, 16, 32, 64); 0 = no slab
+  uint32_t slab_nrf = 0;          // G = 8: fixed gather rounds per group of 32 probes (0 = batches)
   uint64_t slab_granules = 0;
   // device-resident results of the last nq_query_batch_device(out == NULL)
   uint64_t* d_pool = nullptr;

@@ -773,7 +773,9 @@ static cudaError_t launch_query(const nq_index* ix, int mode, size_t smem, unsig
 // (directory rows + posting arrays) must sit in L2.  NQ_QUERY_PF_AHEAD overrides the lead (measurement only).
 static uint32_t query_prefetch_lead(const nq_index* ix, bool slab) {
   static const char* env = nq_tuning_env("NQ_QUERY_PF_AHEAD");
-  const uint32_t lead = env ? (uint32_t)atoi(env) : kPfAhead;
+  // (slab form: off by default — the CTAs of a launch drift apart by more cells than L2 holds, and
+  // the gathers of the laggards then pay for the prefetch AND their own misses: 0.77 vs 0.68 ms)
+  const uint32_t lead = env ? (uint32_t)atoi(env) : slab ? 0u : kPfAhead;
   const uint64_t chunk = slab ? (uint64_t)kPfCells * (ix->p.range / 32) * 16 + ix->slab_granules * ix->slab_G * 2 / ix->p.F * kPfCells
                               : (uint64_t)kPfCells * ((uint64_t)ix->row_stride * 2 + ix->gid_stride) * ix->elem;
   return (lead + 1) * chunk <= (64ull << 20) ? lead : 0u;
@@ -792,7 +794,8 @@ static uint64_t query_wave(const nq_index* ix, int mode, size_t smem, const Quer
   // every query over `parts` CTAs instead (set_query_parts)
   if (mode == kGlobal32) return std::max<uint64_t>(1, std::min<uint64_t>(nq, (64ull << 20) / ((uint64_t)ix->n * 4)));
   static const char* env = nq_tuning_env("NQ_QUERY_WAVES");  // "0": one grid (measurement only)
-  if (!a.prefetch || (env && env[0] == '0')) return nq;
+  // (the slab form is always cut into waves: its descriptor scratch is sized by the launch and stays in L2)
+  if (!a.slab && (!a.prefetch || (env && env[0] == '0'))) return nq;
   int occ = 0;
   if (launch_query(ix, mode, smem, 1, a, 0, nullptr, &occ) != cudaSuccess || occ <= 0) return nq;
   static const char* cap_env = nq_tuning_env("NQ_QUERY_WAVE_SM");  // cap of resident queries per SM in a wave (measurement only)
@@ -887,6 +890,10 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
 
   const uint64_t q_per_launch = query_wave(ix, mode, smem, a, nq);
   if (set_query_parts(ix, mode, q_per_launch, a) != NQ_OK) { nq_dfree(ctx, a.slice_hits); delete hits; return NQ_ERR_CUDA; }
+  if (slab) {  // descriptor scratch of one launch + the prefetch claims behind it
+    if (nq_dmalloc(ctx, (void**)&a.desc, (q_per_launch * p.F + p.F / 256 + 16) * sizeof(uint32_t)) != NQ_OK) { delete hits; return NQ_ERR_CUDA; }
+    a.pf_claim = a.desc + q_per_launch * p.F;
+  }
 
   unsigned long long* d_cursor = nullptr;
   uint64_t* d_begin = nullptr;
@@ -895,7 +902,7 @@ int nq_query_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t
   int st = NQ_OK;
   auto cleanup = [&]() {
     nq_dfree(ctx, d_cursor); nq_dfree(ctx, d_begin); nq_dfree(ctx, d_n); nq_dfree(ctx, d_gcounts);
-    nq_dfree(ctx, a.slice_hits); nq_dfree(ctx, a.slice_base);
+    nq_dfree(ctx, a.slice_hits); nq_dfree(ctx, a.slice_base); nq_dfree(ctx, a.desc);
   };
   auto fail = [&](int s) {
     cleanup();
@@ -1003,6 +1010,10 @@ int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, ui
   if (const char* ex = nq_tuning_env("NQ_QUERY_EXP")) a.exp = (uint32_t)atoi(ex);
   const uint64_t q_per_launch = query_wave(ix, mode, smem, a, nq);
   if (set_query_parts(ix, mode, q_per_launch, a) != NQ_OK) { nq_dfree(ctx, a.slice_hits); return NQ_ERR_CUDA; }
+  if (slab) {
+    NQ_TRY(nq_dmalloc(ctx, (void**)&a.desc, (q_per_launch * p.F + p.F / 256 + 16) * sizeof(uint32_t)));
+    a.pf_claim = a.desc + q_per_launch * p.F;
+  }
   unsigned long long* d_cursor = nullptr;  // [1] = gather statistics
   NQ_TRY(nq_dmalloc(ctx, (void**)&d_cursor, 16));
   if (mode == kGlobal32) {
@@ -1024,6 +1035,7 @@ int nq_query_dense_impl(nq_index* ix, const int32_t* d_sketches, uint64_t nq, ui
   nq_dfree(ctx, a.gcounts);
   nq_dfree(ctx, a.slice_hits);
   nq_dfree(ctx, a.slice_base);
+  nq_dfree(ctx, a.desc);
   if (e != cudaSuccess) return nq_set_error(NQ_ERR_CUDA, "matrix row kernel launch failed: %s", cudaGetErrorString(e));
   return NQ_OK;
 }

@@ -29,6 +29,8 @@ struct QueryArgs {
   const uint2* slab;       //   granules in 8-byte units
   const uint32_t* cell_gran;  // [F+1] first granule of each cell (prefetch windows)
   uint32_t mgroups;        //   range / 32
+  uint32_t* desc;          //   scratch [queries per launch][F]: resolved probes (slab.cu step 1)
+  uint32_t* pf_claim;      //   scratch [F / 256 + 16]: prefetch slices handed out per chunk of cells
   uint32_t exp;            // measurement builds only (NQ_TUNING): experiment bits
   uint32_t* dense;      // when set: row q of [nq][n] takes every genome's count instead of the thresholded hit list (--matrix)
 };

@@ -14,16 +14,9 @@
 
 #include "device_common.cuh"
 #include "internal.h"
+#include "sketch_common.cuh"
 
 namespace nq {
-
-struct Span {
-  uint64_t kb;     // first k-mer start of the span (byte offset into the bases buffer)
-  uint64_t ke;     // one past the last k-mer start
-  uint64_t e0;     // first byte of the entry
-  uint32_t entry;  // sketch row
-  uint32_t pad;
-};
 
 // char -> (forward code, complement code pre-shifted to its place in the reverse strand).
 // nuc2int (:114-123): C,G,T -> 1,2,3, anything else 0.  nuc2intrc (:211-221): A,C,G -> 3,2,1,
@@ -40,61 +33,6 @@ __device__ __forceinline__ uint32_t seed_code(uint32_t c) {
     case 'T': case 't': return 3;
     default: return 4;
   }
-}
-
-struct KmerState {
-  uint64_t f, r;
-};
-
-template <bool SMEM>
-struct SketchSink {
-  uint32_t* sk;  // shared (SMEM) or global sketch row
-  // global form only: coarse shared-memory filter, `fbits` (0, 4 or 8) bits per cell holding an upper
-  // bound of the top bits (fp >> cshift) of the smallest fingerprint this CTA has SUBMITTED to the
-  // cell.  A k-mer whose top bits are above it cannot lower the cell and skips the global access.
-  // Updates are plain (racy) stores: a lost or stale update only leaves a bound that is too high,
-  // i.e. a more permissive filter — every value ever stored is the top bits of a submitted fingerprint.
-  uint8_t* filt;
-  uint32_t fbits, cshift;
-  __device__ __forceinline__ void update(uint32_t b, uint32_t fp) const {
-    // sketch[b] = min(sketch[b], fp) with empty = 0xFFFFFFFF (:350-355).
-    if (SMEM) {
-      // shared memory: a fire-and-forget ATOMS.MIN per k-mer is cheaper than read + compare +
-      // conditional atomic (measured on B200: 563 vs 517 Gbases/s)
-      atomicMin(&sk[b], fp);
-    } else {
-      if (fbits == 8) {
-        const uint32_t c = min(fp >> cshift, 255u), cur = filt[b];
-        if (c > cur) return;
-        if (c < cur) filt[b] = (uint8_t)c;
-      } else if (fbits == 4) {
-        const uint32_t byte = filt[b >> 1], sh = (b & 1u) * 4u, cur = (byte >> sh) & 15u, c = min(fp >> cshift, 15u);
-        if (c > cur) return;
-        if (c < cur) filt[b >> 1] = (uint8_t)((byte & ~(15u << sh)) | (c << sh));
-      }
-      // global memory: a plain read filters out the k-mers that cannot lower the cell; a
-      // stale read only makes the filter conservative because cells never increase
-      if (fp < sk[b]) atomicMin(&sk[b], fp);
-    }
-  }
-};
-
-// (hi:lo) * (Ch:Cl) mod 2^64 as a chain of three multiply-adds with 32-bit addends (IMAD.WIDE,
-// IMAD, IMAD): no zeroed register pair, no separate add.  PTX pins the association.
-__device__ __forceinline__ uint2 mul64c(uint32_t hi, uint32_t lo, uint32_t Ch, uint32_t Cl) {
-  uint32_t plo, phi;
-  asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(plo), "=r"(phi) : "r"(lo), "r"(Cl));
-  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(phi) : "r"(lo), "r"(Ch));
-  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(phi) : "r"(hi), "r"(Cl));
-  return make_uint2(plo, phi);
-}
-// high word only: IMAD.HI, IMAD, IMAD
-__device__ __forceinline__ uint32_t mul64c_hi_chain(uint32_t hi, uint32_t lo, uint32_t Ch, uint32_t Cl) {
-  uint32_t r;
-  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(lo), "r"(Cl));
-  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r) : "r"(lo), "r"(Ch));
-  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r) : "r"(hi), "r"(Cl));
-  return r;
 }
 
 // DEF = the default parameter set K=31, W=12, H=4 (M=8, mask_M=255, maxrem=15): masks and shifts
@@ -478,6 +416,8 @@ static DevParams make_dev_params(const nq_params* p) {
 }  // namespace nq
 
 using namespace nq;
+
+DevParams nq_make_dev_params(const nq_params* p) { return make_dev_params(p); }
 
 template <bool SMEM, int NT, bool RC_HI, bool SMALL_REM, bool DEF>
 static int launch_scan_t(nq_ctx* ctx, const DevParams& P, const uint8_t* d_bases, const uint64_t* d_offsets,

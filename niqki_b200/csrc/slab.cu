@@ -32,22 +32,24 @@ constexpr uint32_t kSlabPads = 32;  // padding ids n .. n+31
 __host__ __device__ __forceinline__ uint32_t slab_pad(uint32_t n, uint32_t fp, uint32_t k) { return n + ((fp + k) & 31u); }
 
 // ---- build ---------------------------------------------------------------------------------------
-// size-biased mean list length over a sample of cells: sums[0] += len, sums[1] += len^2
+// size-biased list statistics over a sample of cells: sums[0] += len, sums[1] += len^2, sums[3] += len * granules(G=8)
 __global__ void __launch_bounds__(256) slab_stat_kernel(const uint32_t* __restrict__ dir, uint32_t row_stride, uint32_t range,
                                                         uint32_t F, uint32_t cells, unsigned long long* __restrict__ sums) {
   const uint32_t cell = (uint32_t)((uint64_t)blockIdx.x * F / cells);
   const uint32_t* row = dir + (size_t)cell * row_stride;
-  unsigned long long s1 = 0, s2 = 0;
+  unsigned long long s1 = 0, s2 = 0, s3 = 0;
   for (uint32_t f = threadIdx.x; f < range; f += blockDim.x) {
     const uint32_t w = row[f], len = (w >> 16) - (w & 0xFFFFu);
     s1 += len; s2 += (unsigned long long)len * len;
+    s3 += (unsigned long long)len * min(3u, (len + 7) / 8);  // granules a probe of this list gathers at G = 8
   }
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
     s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, d);
     s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, d);
+    s3 += __shfl_xor_sync(0xFFFFFFFFu, s3, d);
   }
-  if ((threadIdx.x & 31) == 0 && s1) { atomicAdd(sums, s1); atomicAdd(sums + 1, s2); }
+  if ((threadIdx.x & 31) == 0 && s1) { atomicAdd(sums, s1); atomicAdd(sums + 1, s2); atomicAdd(sums + 3, s3); }
 }
 
 struct SlabGroup { uint32_t b0, b1, b2, gran; };
@@ -190,80 +192,149 @@ __global__ void slab_dummy_kernel(uint16_t* __restrict__ slab, uint32_t G, uint3
 // ---- query ---------------------------------------------------------------------------------------
 constexpr uint32_t kSlabPfCells = 256;  // cells per prefetch chunk
 
-// this CTA's slice of a region, cut into <= 32 bulk requests (one per lane of warp 0)
-__device__ __forceinline__ void slab_prefetch_region(const char* base, uint64_t bytes, uint32_t lane) {
-  const uint64_t per_cta = ((bytes + gridDim.x - 1) / gridDim.x + 15) & ~15ull;
-  const uint64_t lo = (uint64_t)blockIdx.x * per_cta;
-  if (lo >= bytes) return;
-  const uint32_t mine = (uint32_t)min(per_cta, bytes - lo);
-  const uint32_t piece = max(2048u, ((mine + 31) / 32 + 15) & ~15u);
-  const uint32_t o = lane * piece;
-  if (o < mine) l2_prefetch_bulk(base + lo + o, (min(piece, mine - o) + 15) & ~15u);
-}
+// Cooperative L2 prefetch of the granules of upcoming cells, driven by whoever gets there first:
+// the CTAs of a launch sweep the cells in roughly the same order, and the first kSlabPfSlices of
+// them to enter chunk c (kSlabPfCells cells) each pull one slice of chunk c + lead into L2 through
+// the bulk-copy engine.  DRAM then sees long sequential reads (the slab is read about once per
+// launch) and the 16-byte gathers of every query hit L2, whatever the spread between the fastest and
+// the slowest CTA.  claim[] is zeroed before the launch.  Purely a hint.
+constexpr uint32_t kSlabPfSlices = 64;
 template <int G>
-__device__ __forceinline__ void slab_prefetch_chunk(const QueryArgs& a, uint32_t chunk, uint32_t lane) {
+__device__ __forceinline__ void slab_prefetch_claim(const QueryArgs& a, uint32_t chunk, uint32_t lane) {
   const uint32_t c0 = chunk * kSlabPfCells;
   if (c0 >= a.F) return;
+  uint32_t t = 0;
+  if (lane == 0) t = atomicAdd(a.pf_claim + chunk, 1u);
+  t = __shfl_sync(0xFFFFFFFFu, t, 0);
+  if (t >= kSlabPfSlices) return;
   const uint32_t c1 = min(a.F, c0 + kSlabPfCells);
-  slab_prefetch_region(reinterpret_cast<const char*>(a.meta + (size_t)c0 * a.mgroups), (uint64_t)(c1 - c0) * a.mgroups * 16, lane);
-  const uint32_t g0 = __ldg(a.cell_gran + c0), g1 = __ldg(a.cell_gran + c1);
-  slab_prefetch_region(reinterpret_cast<const char*>(a.slab) + (size_t)g0 * (G * 2), (uint64_t)(g1 - g0) * (G * 2), lane);
+  const uint64_t g0 = __ldg(a.cell_gran + c0), g1 = __ldg(a.cell_gran + c1);
+  const uint64_t bytes = (g1 - g0) * (G * 2);
+  const uint64_t per = ((bytes + kSlabPfSlices - 1) / kSlabPfSlices + 15) & ~15ull, lo = (uint64_t)t * per;
+  if (lo >= bytes) return;
+  const uint32_t mine = (uint32_t)min(per, bytes - lo);
+  const uint32_t piece = ((mine + 31) / 32 + 15) & ~15u, o = lane * piece;
+  if (o < mine)
+    l2_prefetch_bulk(reinterpret_cast<const char*>(a.slab) + g0 * (G * 2) + lo + o, (min(piece, mine - o) + 15) & ~15u);
 }
 
-template <int MODE, int NT, int G>
-__global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : NT == 512 ? 2 : 1) query_slab_kernel(QueryArgs a, uint64_t q0) {
-  static_assert(MODE == kPack16 || MODE == kSmem32, "shared-memory counters");
+// ---- step 1: resolve.  desc[q][cell] = first granule (29 bits) | granules inline (2 bits) | tail flag of
+// the list that query q probes in `cell`.  One lane per cell, four probes in flight per lane and no
+// shared memory, so the SMs are full of warps that do nothing but cover the latency of the meta reads
+// (inside the counting kernel the same reads sat in front of every group with one load in flight).
+constexpr uint32_t kDescOffBits = 29;
+constexpr uint32_t kDescOffMask = (1u << kDescOffBits) - 1u;
+
+__global__ void __launch_bounds__(256) slab_resolve_kernel(QueryArgs a, uint64_t q0, uint32_t nqb, uint32_t* __restrict__ desc) {
+  constexpr int U = 4;
+  const uint32_t lane = threadIdx.x & 31;
+  // warps in cell-major order: neighbouring warps resolve the same 128 cells for different queries, so
+  // the meta rows of those cells are read from DRAM once and then found in L2
+  const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t wpq = (a.F + 32 * U - 1) / (32 * U);  // warps per query
+  if (gw >= (uint64_t)wpq * nqb) return;
+  const uint64_t ql = gw % nqb;
+  const uint32_t c0 = (uint32_t)(gw / nqb) * (32 * U);
+  const int32_t* sk = a.qsk + (q0 + ql) * a.F;
+  uint32_t fp[U];
+  uint4 mw[U];
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const uint32_t cell = c0 + 32 * k + lane;
+    fp[k] = cell < a.F ? (uint32_t)__ldcs(&sk[cell]) : 0xFFFFFFFFu;  // read once: streaming
+  }
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const uint32_t cell = min(c0 + 32 * k + lane, a.F - 1);
+    mw[k] = __ldg(a.meta + (size_t)cell * a.mgroups + (min(fp[k], a.range - 1) >> 5));
+  }
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const uint32_t cell = c0 + 32 * k + lane;
+    const uint32_t sh = fp[k] & 31u, lt = (1u << sh) - 1u;
+    uint32_t d = 0;
+    if (fp[k] < a.range) {
+      const uint32_t cls = ((mw[k].x >> sh) & 1u) + 2u * ((mw[k].y >> sh) & 1u), ext = (mw[k].z >> sh) & 1u;
+      const uint32_t off = mw[k].w + __popc(mw[k].x & lt) + 2 * __popc(mw[k].y & lt) + __popc(mw[k].z & lt);
+      d = cls ? off | (cls << kDescOffBits) | (ext << 31) : 0u;
+    }
+    if (cell < a.F) desc[ql * a.F + cell] = d;
+  }
+}
+
+// ---- step 2: gather + count.  A warp takes 32 cells of its query per group: descriptors (coalesced,
+// fetched ahead), two ballots place every list's granules in the group's work list, rounds of 32 lanes x
+// 8 bytes gather whole granules, a register ring keeps D batches in flight, ids are counted with shared-
+// memory atomics.  MODE kDual16 (S <= 15): the CTA counts TWO queries, warps [0, NW/2) the first and
+// [NW/2, NW) the second, into one u32 word per genome — low half-word = first query (a count never
+// exceeds F <= 32768, so it cannot carry) — which makes counting an id `min, shift, ATOMS` with a
+// per-warp constant increment instead of picking the half-word of a packed pair.  Padding ids (>= n) are
+// clamped to n + lane: 32 spare words, one bank each.
+// NRF > 0 (G = 8, short lists): a group's granules are gathered in exactly NRF rounds of straight-line
+// code (16 granules each; slots past the group's total read the dummy granule), kept in a ring of D
+// groups; the rare group with more granules takes its extra rounds on the spot.  NRF = 0: batches of R
+// rounds as the lists need them.
+template <int MODE, int NT, int G, int NRF>
+__global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : NT == 512 ? 2 : 1)
+query_slab_kernel(QueryArgs a, uint64_t q0, uint32_t nqb, const uint32_t* __restrict__ desc) {
+  static_assert(MODE == kDual16 || MODE == kSmem32, "shared-memory counters, one word per genome");
+  constexpr bool DUAL = MODE == kDual16;
+  constexpr int NW = NT / 32, NWQ = DUAL ? NW / 2 : NW;  // warps per query
   constexpr int LPG = G / 4;     // lanes per granule: every lane takes 8 bytes = 4 ids
   constexpr int GPR = 32 / LPG;  // granules per round
-  constexpr int R = 4, D = 3;    // rounds per batch, batches in the register ring
-  constexpr int TAB = 96 + GPR;  // <= 3 granules per cell + the dead tail of the last round
+  constexpr int R = NRF ? NRF : 4, D = 3;  // rounds per ring slot, slots in the register ring
+  constexpr int TAB = 96 + GPR * (NRF ? NRF : 1);  // <= 3 granules per cell + the dead tail
+  constexpr int AHEAD = 3;       // descriptor groups in flight
   extern __shared__ __align__(16) uint32_t smem[];
-  __shared__ uint32_t s_tab[NT / 32][TAB];
-  const uint64_t q = q0 + blockIdx.x;
+  __shared__ uint32_t s_tab[NW][TAB];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t words = MODE == kPack16 ? (a.n + kSlabPads + 1) / 2 : a.n + kSlabPads;
+  const uint32_t half = DUAL ? warp / NWQ : 0, qwarp = DUAL ? warp % NWQ : warp;
+  const uint32_t ql = blockIdx.x * (DUAL ? 2 : 1) + half;  // query inside the launch
+  const bool have_q = ql < nqb;
+  const uint32_t n = a.n;
   constexpr unsigned kFull = 0xFFFFFFFFu;
 
   if (warp == 0 && a.prefetch)
-    for (uint32_t ch = 0; ch < a.prefetch; ++ch) slab_prefetch_chunk<G>(a, ch, lane);
-  for (uint32_t i = tid; i < words; i += NT) smem[i] = 0;
+    for (uint32_t ch = 0; ch < a.prefetch; ++ch) slab_prefetch_claim<G>(a, ch, lane);
+  for (uint32_t i = tid; i < n + kSlabPads; i += NT) smem[i] = 0;
   __syncthreads();
 
-  const int32_t* sk = a.qsk + q * a.F;
+  const uint32_t F = have_q ? a.F : 0;  // a CTA's missing second query walks no cells
+  const uint32_t* dq = desc + (size_t)(have_q ? ql : 0) * a.F;
   uint32_t* tab = s_tab[warp];
   const uint32_t sub = lane % LPG, grp = lane / LPG;
   const unsigned below = (1u << lane) - 1;
+  const uint32_t inc = half ? 0x10000u : 1u;
+  const uint32_t pad = n + lane;  // padding ids (>= n) are clamped to one spare word per lane: min, shift, ATOMS
 #ifdef NQ_TUNING
   uint32_t sink = 0;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
 #endif
+  auto count1 = [&](uint32_t id) {
+#ifdef NQ_TUNING
+    if (a.exp & 4u) { red_shared_add_if_lt(sbase + id * 4u, inc, id, n); return; }  // experiment: predicated instead of clamped
+#endif
+    atomicAdd(&smem[min(id, pad)], inc);
+  };
   auto count2 = [&](uint32_t w) {  // two ids in one word
 #ifdef NQ_TUNING
     if (a.exp & 1u) { sink ^= w; return; }  // experiment: gathers without counting
 #endif
-    if (MODE == kPack16) {
-      atomicAdd(&smem[(w & 0xFFFFu) >> 1], (w & 1u) ? 0x10000u : 1u);
-      atomicAdd(&smem[w >> 17], (w & 0x10000u) ? 0x10000u : 1u);
-    } else {
-      atomicAdd(&smem[w & 0xFFFFu], 1u);
-      atomicAdd(&smem[w >> 16], 1u);
-    }
+    count1(w & 0xFFFFu);
+    count1(w >> 16);
   };
-  auto count1 = [&](uint32_t id) {
-    if (MODE == kPack16) atomicAdd(&smem[id >> 1], (id & 1u) ? 0x10000u : 1u);
-    else atomicAdd(&smem[id], 1u);
+  auto load_gran = [&](uint32_t g) -> uint2 {
+#ifdef NQ_TUNING
+    if (a.exp & 2u) return make_uint2((g * 0x10003u) % n * 0x10001u, (g * 7u) % n * 0x10001u);  // experiment: no gathers
+#endif
+    return __ldg(a.slab + (g * (uint32_t)LPG + sub));
   };
 
-  // software pipeline over the warp's groups of 32 cells: fingerprints two groups ahead, meta words
-  // one group ahead, granule gathers D-1 batches ahead of their counting
-  const uint32_t step = NT;
-  uint32_t c_cur = warp * 32;
-  auto probe = [&](uint32_t cell, uint32_t fp) {  // clamped into the table; fp >= range is masked at decode
-    return __ldg(a.meta + (size_t)min(cell, a.F - 1) * a.mgroups + (min(fp, a.range - 1) >> 5));
-  };
-  uint32_t fp_cur = 0xFFFFFFFFu, fp_next = 0xFFFFFFFFu, fp_next2;
-  if (c_cur + lane < a.F) fp_cur = (uint32_t)__ldg(&sk[c_cur + lane]);
-  if (c_cur + step + lane < a.F) fp_next = (uint32_t)__ldg(&sk[c_cur + step + lane]);
-  uint4 mw = probe(c_cur + lane, fp_cur), mw_next;
+  const uint32_t step = NWQ * 32;
+  uint32_t c_cur = qwarp * 32;
+  uint32_t dn[AHEAD];  // descriptors of the next AHEAD groups
+#pragma unroll
+  for (int k = 0; k < AHEAD; ++k) dn[k] = c_cur + k * step + lane < F ? __ldcs(&dq[c_cur + k * step + lane]) : 0u;
 
   uint2 lbuf[D][R];
   uint32_t live[D];
@@ -281,20 +352,13 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : NT == 512 
     }
   };
   auto gather = [&](uint2 (&l)[R], const uint32_t* t0, uint32_t nb) {
-#ifdef NQ_TUNING
-    if (a.exp & 2u) {  // experiment: counting without gathers (ids made up from the table)
-#pragma unroll
-      for (int k = 0; k < R; ++k) l[k] = make_uint2((t0[k * GPR + grp] * 0x10003u) % a.n * 0x10001u, (t0[k * GPR + grp] * 7u) % a.n * 0x10001u);
-      return;
-    }
-#endif
     if (nb >= (uint32_t)R) {
 #pragma unroll
-      for (int k = 0; k < R; ++k) l[k] = __ldg(a.slab + (t0[k * GPR + grp] * (uint32_t)LPG + sub));
+      for (int k = 0; k < R; ++k) l[k] = load_gran(t0[k * GPR + grp]);
     } else {
 #pragma unroll
       for (int k = 0; k < R - 1; ++k)
-        if ((uint32_t)k < nb) l[k] = __ldg(a.slab + (t0[k * GPR + grp] * (uint32_t)LPG + sub));
+        if ((uint32_t)k < nb) l[k] = load_gran(t0[k * GPR + grp]);
     }
   };
   auto batch = [&](const uint32_t* t0, uint32_t nb) {
@@ -309,55 +373,96 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 8 : NT == 256 ? 4 : NT == 512 
     phase = phase + 1 == (uint32_t)D ? 0 : phase + 1;
   };
 
-  for (; c_cur < a.F; c_cur += step) {
-    if (warp == 0 && a.prefetch && c_cur % kSlabPfCells == 0) slab_prefetch_chunk<G>(a, c_cur / kSlabPfCells + a.prefetch, lane);
-    fp_next2 = 0xFFFFFFFFu;
-    if (c_cur + 2 * step + lane < a.F) fp_next2 = (uint32_t)__ldg(&sk[c_cur + 2 * step + lane]);
-    mw_next = probe(c_cur + step + lane, fp_next);
+  // one group of 32 cells: its granules go into ring slot `gb` (NRF) or through batch(); the slot filled
+  // D-1 groups ago (`cb`) is counted while these gathers fly
+  auto group = [&](uint2 (&gb)[R], uint2 (&cb)[R], bool& cb_live, bool& gb_live) {
+    if (warp == 0 && a.prefetch && c_cur % kSlabPfCells == 0) slab_prefetch_claim<G>(a, c_cur / kSlabPfCells + a.prefetch, lane);
+    const uint32_t d = dn[0];
+#pragma unroll
+    for (int k = 0; k + 1 < AHEAD; ++k) dn[k] = dn[k + 1];
+    dn[AHEAD - 1] = c_cur + AHEAD * step + lane < F ? __ldcs(&dq[c_cur + AHEAD * step + lane]) : 0u;
 
-    // decode: granule count (0..3) and first granule of this lane's list
-    const uint32_t sh = fp_cur & 31u, lt = (1u << sh) - 1u;
-    const bool valid = fp_cur < a.range;
-    const uint32_t c0 = valid ? (mw.x >> sh) & 1u : 0u, c1 = valid ? (mw.y >> sh) & 1u : 0u;
-    const uint32_t ce = valid ? (mw.z >> sh) & 1u : 0u;
-    const uint32_t off = mw.w + __popc(mw.x & lt) + 2 * __popc(mw.y & lt) + __popc(mw.z & lt);
-    const unsigned bal0 = __ballot_sync(kFull, c0), bal1 = __ballot_sync(kFull, c1), bale = __ballot_sync(kFull, ce);
+    const uint32_t off = d & kDescOffMask, c0 = (d >> kDescOffBits) & 1u, c1 = (d >> (kDescOffBits + 1)) & 1u;
+    const unsigned bal0 = __ballot_sync(kFull, c0), bal1 = __ballot_sync(kFull, c1), bale = __ballot_sync(kFull, d >> 31);
     const uint32_t excl = __popc(bal0 & below) + 2 * __popc(bal1 & below);
     const uint32_t total = __popc(bal0) + 2 * __popc(bal1);
     if (c0 | c1) tab[excl] = off;
     if (c1) tab[excl + 1] = off + 1;
     if (c0 & c1) tab[excl + 2] = off + 2;
-    if (lane < GPR) tab[total + lane] = 0;  // dead slots of the last round gather the dummy granule
+    if (NRF) {
+      // dead slots up to the fixed rounds (and of the last extra round) gather the dummy granule
+      for (uint32_t i = total + lane; i < max((uint32_t)(NRF * GPR), (total + GPR - 1) / GPR * GPR); i += 32) tab[i] = 0;
+    } else if (lane < GPR) {
+      tab[total + lane] = 0;
+    }
     __syncwarp();
-    const uint32_t rounds = (total + GPR - 1) / GPR;
-    for (uint32_t r0 = 0; r0 < rounds; r0 += R) batch(tab + r0 * GPR, min((uint32_t)R, rounds - r0));
+    if (NRF) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) gb[k] = load_gran(tab[k * GPR + grp]);
+      gb_live = true;
+      if (cb_live) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) { count2(cb[k].x); count2(cb[k].y); }
+        cb_live = false;
+      }
+      for (uint32_t r = NRF * GPR; r < total; r += GPR) {  // rare: more granules than the fixed rounds hold
+        const uint2 v = load_gran(tab[r + grp]);
+        count2(v.x); count2(v.y);
+      }
+    } else {
+      const uint32_t rounds = (total + GPR - 1) / GPR;
+      for (uint32_t r0 = 0; r0 < rounds; r0 += R) batch(tab + r0 * GPR, min((uint32_t)R, rounds - r0));
+    }
     if (bale) {  // tails of lists longer than 3 granules (rare): straight from the CSR posting array
       unsigned m = bale;
       while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
         const uint32_t dg = __shfl_sync(kFull, off + 3, src);
-        const uint2 d = __ldg(a.slab + (size_t)dg * LPG);
-        const uint16_t* g = static_cast<const uint16_t*>(a.gids) + (size_t)(c_cur + src) * a.gid_stride + d.x;
-        for (uint32_t i = lane; i < d.y; i += 32) count1(g[i]);
+        const uint2 td = __ldg(a.slab + (size_t)dg * LPG);
+        const uint16_t* g = static_cast<const uint16_t*>(a.gids) + (size_t)(c_cur + src) * a.gid_stride + td.x;
+        for (uint32_t i = lane; i < td.y; i += 32) count1(g[i]);
       }
     }
     __syncwarp();  // the table is rewritten by the next group
-    mw = mw_next;
-    fp_cur = fp_next;
-    fp_next = fp_next2;
-  }
-#pragma unroll
-  for (int i = 1; i < D; ++i) {
+    c_cur += step;
+  };
+
+  if (NRF) {
+    bool lv[D] = {false, false, false};
+    while (c_cur < F) {
+      group(lbuf[0], lbuf[1], lv[1], lv[0]);
+      if (c_cur >= F) break;
+      group(lbuf[1], lbuf[2], lv[2], lv[1]);
+      if (c_cur >= F) break;
+      group(lbuf[2], lbuf[0], lv[0], lv[2]);
+    }
 #pragma unroll
     for (int p = 0; p < D; ++p)
-      if (phase == (uint32_t)p) drain(lbuf[(p + i) % D], live[(p + i) % D]);
+      if (lv[p]) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) { count2(lbuf[p][k].x); count2(lbuf[p][k].y); }
+      }
+  } else {
+    bool unused0 = false, unused1 = false;
+    while (c_cur < F) group(lbuf[0], lbuf[0], unused0, unused1);
+#pragma unroll
+    for (int i = 1; i < D; ++i) {
+#pragma unroll
+      for (int p = 0; p < D; ++p)
+        if (phase == (uint32_t)p) drain(lbuf[(p + i) % D], live[(p + i) % D]);
+    }
   }
   __syncthreads();
 #ifdef NQ_TUNING
   if (sink == 0x12345u) smem[0] = sink;
 #endif
-  query_finish<MODE, NT, true>(a, q, smem, 0, 0);
+  const uint64_t qa = q0 + (uint64_t)blockIdx.x * (DUAL ? 2 : 1);
+  query_finish<MODE, NT, true>(a, qa, smem, 0, 0);
+  if (DUAL && qa + 1 < q0 + nqb) {
+    __syncthreads();
+    query_finish<MODE, NT, true>(a, qa + 1, smem, 0, 16);
+  }
 }
 
 }  // namespace nq
@@ -376,10 +481,11 @@ void nq_slab_free(nq_index* ix) {
 // shared-memory counters of the slab kernel: n + 32 padding ids, packed u16 when S <= 15
 bool nq_slab_layout(const nq_index* ix, int& mode, size_t& smem) {
   const size_t fixed = 8 * 1024, optin = ix->ctx->smem_optin;
-  const size_t pack = (size_t)((ix->n + kSlabPads + 1) / 2) * 4, full = (size_t)(ix->n + kSlabPads) * 4;
-  if (ix->p.S <= 15 && pack + fixed <= optin) { mode = kPack16; smem = pack; return true; }
-  if (full + fixed <= optin) { mode = kSmem32; smem = full; return true; }
-  return false;
+  const size_t full = (size_t)(ix->n + kSlabPads) * 4;  // one u32 word per genome (+ 32 spare): two queries (S <= 15) or one
+  if (full + fixed > optin) return false;
+  mode = ix->p.S <= 15 ? kDual16 : kSmem32;
+  smem = full;
+  return true;
 }
 
 int nq_slab_build(nq_index* ix) {
@@ -403,19 +509,32 @@ int nq_slab_build(nq_index* ix) {
     return st;
   };
   cudaError_t e;
-  unsigned long long sums[3] = {0, 0, 0};
+  unsigned long long sums[4] = {0, 0, 0, 0};
   const uint32_t sample = std::min<uint32_t>(F, 512);
   if ((e = cudaMemsetAsync(d_sums, 0, 32, ctx->stream)) != cudaSuccess) return fail(nq_set_error(NQ_ERR_CUDA, "memset failed"));
   slab_stat_kernel<<<sample, 256, 0, ctx->stream>>>(dir, ix->row_stride, range, F, sample, d_sums);
   ctx->launches++;
-  if ((e = cudaMemcpyAsync(sums, d_sums, 16, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+  if ((e = cudaMemcpyAsync(sums, d_sums, 32, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
       (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
     return fail(nq_set_error(NQ_ERR_CUDA, "slab statistics failed: %s", cudaGetErrorString(e)));
   // ids per granule ~ the length of a probed list (size-biased mean): 1-2 granules per probe
   const double m = sums[0] ? (double)sums[1] / (double)sums[0] : 1.0;
-  uint32_t G = m <= 12.0 ? 8u : m <= 24.0 ? 16u : m <= 48.0 ? 32u : 64u;
+  // Short lists (m <= 12: shards of up to ~15k bacterial genomes at the default W) stay on the CSR kernels of
+  // query.cu: measured on B200 the 8-id granule form loses to them there (1000 queries vs 10k genomes: 0.77 vs
+  // 0.64 ms; 10k vs 12.5k: 7.2 vs 6.6 ms — both forms sit at the L1TEX wavefront rate of an SM, and the CSR
+  // form's sequential L2 prefetch survives the drift between CTAs better), and wins from 16-id granules on
+  // (25k genomes: 8.6 vs 13.3 ms; 50k: 14.2 vs 17.4 ms).
+  uint32_t G = m <= 12.0 ? 0u : m <= 24.0 ? 16u : m <= 48.0 ? 32u : 64u;
   if (env && atoi(env) >= 8) G = (uint32_t)atoi(env);
-  if (G != 8 && G != 16 && G != 32 && G != 64) G = 8;
+#ifdef NQ_TUNING
+  if (G != 0 && G != 8 && G != 16 && G != 32 && G != 64) G = 0;
+#else
+  if (G != 0 && G != 16 && G != 32 && G != 64) G = 0;
+#endif
+  if (G == 0) {
+    nq_dfree(ctx, d_sums);
+    return NQ_OK;
+  }
 
   int st;
   if ((st = nq_dmalloc(ctx, (void**)&d_sizes, (size_t)F * 4)) != NQ_OK ||
@@ -435,7 +554,7 @@ int nq_slab_build(nq_index* ix) {
   const uint64_t granules = sums[2];
   nq_dfree(ctx, d_sizes);
   d_sizes = nullptr;
-  if (granules * (G / 4) >= (1ull << 32)) {  // 32-bit granule arithmetic in the query kernel: fall back to the CSR kernels
+  if (granules + 4 >= (1ull << kDescOffBits)) {  // granule numbers travel in 29 bits of a descriptor: else the CSR kernels
     nq_dfree(ctx, d_sums);
     nq_slab_free(ix);
     return NQ_OK;
@@ -459,53 +578,80 @@ int nq_slab_build(nq_index* ix) {
   nq_dfree(ctx, d_sums);
   ix->slab_G = G;
   ix->slab_granules = granules;
+  // G = 8: rounds of 16 granules a group of 32 probes takes in the count kernel's straight-line path
+  // (mean + ~2 sigma of the granules of 32 probes must fit; groups beyond it take extra rounds)
+  const double gpp = sums[0] ? (double)sums[3] / (double)sums[0] : 1.0;
+  ix->slab_nrf = G == 8 ? (32.0 * gpp + 4.0 <= 32.0 ? 2u : 32.0 * gpp + 4.0 <= 48.0 ? 3u : 4u) : 0u;
+  if (const char* nr = nq_tuning_env("NQ_SLAB_NRF")) ix->slab_nrf = G == 8 ? (uint32_t)atoi(nr) : 0u;
   return NQ_OK;
 }
 
-// ---- launch: CTA size from the shared memory the counters take (the L1 that is left tracks the gathers)
-template <int MODE, int NT, int G>
-static cudaError_t launch_slab_t(size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st, int* occ) {
-  auto k = query_slab_kernel<MODE, NT, G>;
+// ---- launch.  Queries per CTA: 2 (kDual16) or 1.  CTA size and CTAs per SM follow the shared memory the
+// counters take: as many CTAs as leave the SM >= ~56 KB of L1 (outstanding gathers allocate L1 lines: with
+// less, the SM cannot keep enough of them in flight), enforced through the shared-memory carve-out.
+struct SlabCfg { int nt, per_sm, carve; };
+static SlabCfg slab_cfg(const nq_index* ix, int mode, size_t smem, uint64_t nq_total) {
+  const size_t per = smem + 1024 + 2048, sm = 228 * 1024, l1 = 56 * 1024;
+  const int fit = (int)std::max<size_t>(1, std::min<size_t>(8, (sm - l1) / per));
+  SlabCfg c;
+  // threads: 2048 per SM over the resident CTAs (64-register kernels), at least 2 warps per query
+  c.nt = fit >= 8 && mode != kDual16 ? 128 : fit >= 4 ? 256 : fit >= 2 ? 512 : 1024;
+  const char* env = nq_tuning_env("NQ_QUERY_NT");
+  if (env && atoi(env) >= 128) c.nt = atoi(env);
+  c.per_sm = std::max(1, std::min(fit, 2048 / c.nt));
+  c.carve = (int)std::min<size_t>(100, (c.per_sm * per * 100 + sm - 1) / sm + 1);
+  (void)nq_total;
+  return c;
+}
+
+template <int MODE, int NT, int G, int NRF>
+static cudaError_t launch_slab_t(const SlabCfg& cfg, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st, int* occ) {
+  auto k = query_slab_kernel<MODE, NT, G, NRF>;
+  constexpr unsigned QPC = MODE == kDual16 ? 2 : 1;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, NT, smem);
-  k<<<nb, NT, smem, st>>>(a, q0);
+  if ((e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cfg.carve)) != cudaSuccess) return e;
+  if (occ) {  // resident QUERIES per SM (wave sizing), no launch
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, NT, smem);
+    *occ = std::min(*occ, cfg.per_sm) * (int)QPC;
+    return e;
+  }
+  // step 1 (descriptors of the launch's queries), then step 2
+  if (a.prefetch && (e = cudaMemsetAsync(a.pf_claim, 0, (a.F / kSlabPfCells + 16) * sizeof(uint32_t), st)) != cudaSuccess) return e;
+  const uint64_t warps = (uint64_t)nb * ((a.F + 127) / 128);
+  slab_resolve_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(a, q0, nb, a.desc);
+  k<<<(nb + QPC - 1) / QPC, NT, smem, st>>>(a, q0, nb, a.desc);
   return cudaSuccess;
 }
-template <int MODE, int G>
-static cudaError_t launch_slab_nt(int nt, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st, int* occ) {
-  switch (nt) {
-    case 128: return launch_slab_t<MODE, 128, G>(smem, nb, a, q0, st, occ);
-    case 256: return launch_slab_t<MODE, 256, G>(smem, nb, a, q0, st, occ);
-    case 512: return launch_slab_t<MODE, 512, G>(smem, nb, a, q0, st, occ);
-    default: return launch_slab_t<MODE, 1024, G>(smem, nb, a, q0, st, occ);
+template <int MODE, int G, int NRF>
+static cudaError_t launch_slab_nt(const SlabCfg& cfg, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st, int* occ) {
+  switch (cfg.nt) {
+    case 128: if (MODE != kDual16) return launch_slab_t<MODE, MODE == kDual16 ? 256 : 128, G, NRF>(cfg, smem, nb, a, q0, st, occ);  // fallthrough
+    case 256: return launch_slab_t<MODE, 256, G, NRF>(cfg, smem, nb, a, q0, st, occ);
+    case 512: return launch_slab_t<MODE, 512, G, NRF>(cfg, smem, nb, a, q0, st, occ);
+    default: return launch_slab_t<MODE, 1024, G, NRF>(cfg, smem, nb, a, q0, st, occ);
   }
 }
 template <int MODE>
-static cudaError_t launch_slab_g(uint32_t G, int nt, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st, int* occ) {
+static cudaError_t launch_slab_g(uint32_t G, uint32_t nrf, const SlabCfg& cfg, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0, cudaStream_t st, int* occ) {
+  (void)nrf;
   switch (G) {
-    case 8: return launch_slab_nt<MODE, 8>(nt, smem, nb, a, q0, st, occ);
-    case 16: return launch_slab_nt<MODE, 16>(nt, smem, nb, a, q0, st, occ);
-    case 32: return launch_slab_nt<MODE, 32>(nt, smem, nb, a, q0, st, occ);
-    default: return launch_slab_nt<MODE, 64>(nt, smem, nb, a, q0, st, occ);
+#ifdef NQ_TUNING  // 8-id granules only exist in measurement builds (nq_slab_build never picks them)
+    case 8:
+      if (nrf == 2) return launch_slab_nt<MODE, 8, 2>(cfg, smem, nb, a, q0, st, occ);
+      if (nrf == 3) return launch_slab_nt<MODE, 8, 3>(cfg, smem, nb, a, q0, st, occ);
+      if (nrf == 4) return launch_slab_nt<MODE, 8, 4>(cfg, smem, nb, a, q0, st, occ);
+      return launch_slab_nt<MODE, 8, 0>(cfg, smem, nb, a, q0, st, occ);
+#endif
+    case 16: return launch_slab_nt<MODE, 16, 0>(cfg, smem, nb, a, q0, st, occ);
+    case 32: return launch_slab_nt<MODE, 32, 0>(cfg, smem, nb, a, q0, st, occ);
+    default: return launch_slab_nt<MODE, 64, 0>(cfg, smem, nb, a, q0, st, occ);
   }
-}
-
-// CTA size: as many queries per SM as leave >= ~40 KB of L1 beside their counters (8 x 128 threads,
-// 4 x 256, 2 x 512, else one 1024-thread CTA); long batches of small shards prefer 256 threads.
-int nq_slab_cta_threads(const nq_index* ix, size_t smem, uint64_t nq_total) {
-  const char* env = nq_tuning_env("NQ_QUERY_NT");
-  if (env && atoi(env) >= 128) return atoi(env);
-  const size_t per = smem + 1024 + 2048, l1 = 40 * 1024, sm = 228 * 1024;
-  if (8 * per + l1 <= sm && nq_total < (uint64_t)ix->ctx->sm_count * 36) return 128;
-  if (4 * per + l1 <= sm) return 256;
-  if (2 * per + l1 <= sm) return 512;
-  return 1024;
 }
 
 cudaError_t nq_slab_launch(const nq_index* ix, int mode, size_t smem, unsigned nb, const QueryArgs& a, uint64_t q0,
                            cudaStream_t st, int* occ) {
-  const int nt = nq_slab_cta_threads(ix, smem, a.nq_total);
-  return mode == kPack16 ? launch_slab_g<kPack16>(ix->slab_G, nt, smem, nb, a, q0, st, occ)
-                         : launch_slab_g<kSmem32>(ix->slab_G, nt, smem, nb, a, q0, st, occ);
+  const SlabCfg cfg = slab_cfg(ix, mode, smem, a.nq_total);
+  return mode == kDual16 ? launch_slab_g<kDual16>(ix->slab_G, ix->slab_nrf, cfg, smem, nb, a, q0, st, occ)
+                         : launch_slab_g<kSmem32>(ix->slab_G, ix->slab_nrf, cfg, smem, nb, a, q0, st, occ);
 }

@@ -6,6 +6,8 @@
 // observable behaviour (genome ids in file/record order == the reference at OMP_NUM_THREADS=1).
 #pragma once
 #include <cstdint>
+#include <future>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -15,7 +17,8 @@
 namespace nqh {
 
 struct EngineOptions {
-  int device = 0;
+  int device = 0;               // first CUDA device
+  int gpus = 1;                 // additive --gpus N: the index is sharded by genome id over devices device..device+N-1
   bool binary_output = false;   // additive --binary: the reference's unreachable binary writer (B9)
   bool matrix_nowrap = false;   // additive --nowrap: 32-bit matrix counters instead of uint16 (B6)
   unsigned reader_threads = 0;  // 0 = hardware concurrency (capped)
@@ -48,27 +51,50 @@ class Engine {
 
  private:
   struct Batch;
+  // One device of the box.  With --gpus N the index is sharded by genome id in contiguous blocks
+  // (nq_shard_range), shard r on device r; sketching work goes round-robin over the devices and
+  // the sketches move to their owner when the index is built.
+  struct Segment { uint32_t gid0, count; uint64_t row; };  // sketches of gids [gid0, gid0+count) at store row `row`
+  struct Shard {
+    nq_ctx* ctx = nullptr;
+    nq_comm* comm = nullptr;
+    nq_index* ix = nullptr;        // posting lists of gids [gid0, gid0+n)
+    uint32_t gid0 = 0, n = 0;
+    int32_t* d_store = nullptr;    // sketches produced on this device since the last build
+    uint64_t store_cap = 0, store_n = 0;
+    std::vector<Segment> segs;
+    int32_t* d_query = nullptr;    // this device's slice of the current query batch
+    uint64_t query_cap = 0;
+    int32_t* d_all = nullptr;      // all-gathered query sketches / broadcast matrix rows
+    uint64_t all_cap = 0;
+  };
   void init_ctx();
-  void flush_insert(Batch& b);
+  template <typename Fn>
+  void on_all_devices(Fn&& fn);   // fn(r) on one host thread per device; rethrows the first failure
+  void submit_insert(Batch& b);   // sketch a batch on the next device (asynchronous with --gpus > 1)
+  void sketch_into_store(int r, Batch& b);
+  void wait_inserts();
+  Batch& insert_batch();          // the batch buffer to fill next
   void flush_query(Batch& b);
-  void ensure_store(uint64_t extra_entries);
+  void reserve_rows(int r, int32_t*& buf, uint64_t& cap, uint64_t rows);
   void build_index();  // posting lists of everything inserted so far (no-op when up to date)
+  void export_all(std::vector<uint32_t>& sizes, std::vector<uint32_t>& gids);  // dump layout over all shards
+  void import_all(const std::vector<uint32_t>& sizes, const std::vector<uint32_t>& gids);
+  uint64_t pending_sketches() const;
   void write_hits(const std::string& name, const uint32_t* counts, const uint32_t* gids, uint64_t n);
   const std::string& frac_text(uint32_t count);
 
   EngineOptions opt_;
   nq_params p_{};
-  nq_ctx* ctx_ = nullptr;
-  nq_index* ix_ = nullptr;          // index over gids [0, indexed_)
-  uint32_t indexed_ = 0;            // genomes covered by ix_
+  std::vector<Shard> sh_;           // one per device
+  bool have_index_ = false;         // shards hold posting lists of gids [0, indexed_)
+  uint32_t indexed_ = 0;            // genomes covered by the index
   uint32_t genome_numbers_ = 0;     // ids handed out so far
   std::vector<std::string> filenames_;
-  // sketches of genomes [store_base_, store_base_+store_n_) waiting in HBM for the next build
-  int32_t* d_store_ = nullptr;
-  uint64_t store_cap_ = 0, store_n_ = 0;
-  uint32_t store_base_ = 0;
-  int32_t* d_query_ = nullptr;  // sketches of the current query batch
-  uint64_t query_cap_ = 0;
+  // insert pipeline: one pinned batch buffer per device, filled by the reader while the others are sketched
+  std::vector<std::unique_ptr<Batch>> ins_batches_;
+  std::vector<std::future<void>> ins_pending_;
+  int ins_cur_ = 0;
   GzWriter out_;
   std::vector<std::string> frac_cache_;
 };

@@ -3,7 +3,7 @@
 // directory behaviour (-I/-i/-M chdir to the list's directory, -Q/-l do not) and the
 // same "Informations" table on stdout.  Behaviour follows the code, not the README, where they
 // differ: --minjac defaults to 0, --querylines' short flag is -l, -P is a no-op
-// and the output is text.  Additive flags: --device N, --binary, --nowrap, --threads N, --verbose.
+// and the output is text.  Additive flags: --device N, --gpus N, --binary, --nowrap, --threads N, --verbose.
 #include <fcntl.h>
 #include <libgen.h>
 #include <limits.h>
@@ -54,7 +54,8 @@ const Flag kFlags[] = {
     {"logo", "", "logo", kNone, "  --logo \tPrint ASCII art logo, then exit."},
     {"help", "h", "help", kNone, "  --help, -h \tPrint usage and exit."},
     // additive
-    {"device", "", "device", kNumeric, "  --device <int> \tCUDA device to run on (0)."},
+    {"device", "", "device", kNumeric, "  --device <int> \tFirst CUDA device to run on (0)."},
+    {"gpus", "", "gpus", kNumeric, "  --gpus <int> \tShard the index by genome id over this many devices (1); queries are all-gathered over NCCL."},
     {"binary", "", "binary", kNone, "  --binary \tWrite query results in the reference's binary record format."},
     {"nowrap", "", "nowrap", kNone, "  --nowrap \tMatrix counters keep 32 bits (the reference wraps at 65536 for S >= 16)."},
     {"threads", "", "threads", kNumeric, "  --threads <int> \tReader threads for file-of-files ingest."},
@@ -186,6 +187,7 @@ int main(int argc, char** argv) {
   std::cout << "+-----------------------------------+-------------------------------+" << std::endl;
   nqh::EngineOptions eo;
   eo.device = has("device") ? atoi(opt["device"].c_str()) : 0;
+  eo.gpus = has("gpus") ? std::max(1, atoi(opt["gpus"].c_str())) : 1;
   eo.binary_output = has("binary");
   eo.matrix_nowrap = has("nowrap");
   eo.reader_threads = has("threads") ? (unsigned)atoi(opt["threads"].c_str()) : 0;

@@ -56,6 +56,10 @@ class Context:
 
     KINDS = ("scan", "densify", "transpose", "cell_sort", "query", "matrix", "slab")
 
+    def set_host_packing(self, mode: int = -1, threads: int = 0):
+        """K1 on the host side of the host-buffer sketch calls: -1 automatic, 0 never, 1 always."""
+        check(self.L.nq_ctx_set_host_packing(self.h, int(mode), int(threads)))
+
     def set_timing(self, on: bool = True):
         check(self.L.nq_ctx_set_timing(self.h, int(on)))
 
@@ -141,6 +145,26 @@ class Index:
             flags = np.zeros(max(n, 1), np.uint32)
         check(self.L.nq_sketch_batch(self.ctx.h, C.byref(self.p), _ptr(bases), _ptr(offsets), n, _ptr(out), _ptr(flags)))
         return out, flags[:n]
+
+    def sketch_records_to_device(self, bases, offsets, out, flags=None, rec_entry=None, n_entries=None):
+        """``nq_sketch_records`` with the sketches left in HBM: host characters in (pinned or pageable;
+        long entries cross PCIe packed to 2 bits per base), ``out`` = device int32 [n_entries][F]."""
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n_rec = offsets.size - 1
+        ne = n_rec if n_entries is None else int(n_entries)
+        bases = np.ascontiguousarray(bases, np.uint8)
+        if flags is None:
+            flags = np.zeros(max(ne, 1), np.uint32)
+        re = None if rec_entry is None else np.ascontiguousarray(rec_entry, np.uint32)
+        check(self.L.nq_sketch_records(self.ctx.h, C.byref(self.p), _ptr(bases), _ptr(offsets), n_rec, _ptr(re), ne, _ptr(out),
+                                       _ptr(flags), 1))
+        return out, flags[:ne]
+
+    def close_index(self):
+        """Free the posting lists (the parameters and the context stay)."""
+        if getattr(self, "ix", None):
+            self.L.nq_index_free(self.ix)
+            self.ix = None
 
     def compute_sketch(self, seq):
         """Index::compute_sketch(reference, sketch) on a fresh sketch -> int32[F]."""

@@ -9,6 +9,12 @@ rank 0 is concatenate + sort by (count, gid) descending — exactly the order
 ``Index::query_sketch`` produces (/root/reference/src/niqki_index.cpp:685).  Thresholding is per
 genome, so it commutes with sharding.
 
+On GPUs the exchange is the library's own: ``Comm`` wraps ``nq_comm_init_rank`` /
+``nq_allgather_sketches`` / ``nq_bcast_sketches`` (NCCL behind the C ABI, u16 on the wire) and
+``merge_hits`` wraps ``nq_hits_merge``; ``torch.distributed`` only carries the 128-byte NCCL id and
+the small per-rank hit lists to rank 0.  ``ShardedIndex`` keeps the same logic over a generic
+``dist`` object so that it also runs on CPU (gloo) in the tests.
+
 The compute object (``engine``) is anything with the ``niqki_b200.Index`` methods used here
 (``compute_sketches`` / ``sketch_many``, ``insert_sketches``, ``query_sketches``); the product
 passes a ``niqki_b200.Index`` (CUDA), the CPU tests pass an adapter.
@@ -119,3 +125,107 @@ class ShardedIndex:
         if self.rank != 0:
             return None
         return merge_hit_lists(parts, nq)
+
+
+# ---- the library's own exchange step (NCCL behind the C ABI) ----------------------------------
+class Comm:
+    """One rank's ``nq_comm`` (include/niqki_b200.h): created from a 128-byte NCCL id made on rank 0
+    and handed to the other ranks by ``bcast_bytes`` (e.g. over torch.distributed)."""
+
+    def __init__(self, ctx, rank: int, world: int, bcast_bytes):
+        import ctypes as C
+
+        from .capi import check, lib
+
+        self.L, self.ctx, self.rank, self.world = lib(), ctx, rank, world
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            check(self.L.nq_comm_unique_id(ident))
+        raw = bcast_bytes(bytes(ident))
+        ident = (C.c_ubyte * 128).from_buffer_copy(raw)
+        h = C.c_void_p()
+        check(self.L.nq_comm_init_rank(ctx.h, ident, world, rank, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nq_comm_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def info(self):
+        import ctypes as C
+
+        from .capi import check
+
+        r, n, v = C.c_int(), C.c_int(), C.c_int()
+        check(self.L.nq_comm_info(self.h, C.byref(r), C.byref(n), C.byref(v)))
+        return dict(rank=r.value, nranks=n.value, nccl_version=v.value)
+
+    def allgather_sketches(self, params, local, out):
+        """``local`` int32 [n_local][F], ``out`` int32 [world*n_local][F]: device tensors."""
+        import ctypes as C
+
+        from .capi import check
+
+        check(self.L.nq_allgather_sketches(self.h, C.byref(params), C.c_void_p(local.data_ptr()), int(local.shape[0]),
+                                           C.c_void_p(out.data_ptr())))
+        return out
+
+    def bcast_sketches(self, params, sketches, root: int):
+        import ctypes as C
+
+        from .capi import check
+
+        check(self.L.nq_bcast_sketches(self.h, C.byref(params), C.c_void_p(sketches.data_ptr()), int(sketches.shape[0]), root))
+        return sketches
+
+
+def torch_bcast_bytes(dist, device):
+    """``bcast_bytes`` for ``Comm`` over an initialised torch.distributed group."""
+
+    def f(raw: bytes) -> bytes:
+        import torch
+
+        t = torch.tensor(list(raw), dtype=torch.uint8, device=device)
+        dist.broadcast(t, src=0)
+        return bytes(t.cpu().tolist())
+
+    return f
+
+
+def merge_hits(parts):
+    """``nq_hits_merge`` over per-shard ``(ptr, counts, gids)`` triples of the same query batch."""
+    import ctypes as C
+
+    from .capi import check, lib
+
+    L = lib()
+    nq = len(parts[0][0]) - 1
+    handles = (C.c_void_p * len(parts))()
+    keep = []
+    for i, (p, c, g) in enumerate(parts):
+        p = np.ascontiguousarray(p, np.uint64)
+        c = np.ascontiguousarray(c if len(c) else np.zeros(1, np.uint32), np.uint32)
+        g = np.ascontiguousarray(g if len(g) else np.zeros(1, np.uint32), np.uint32)
+        keep.append((p, c, g))
+        h = C.c_void_p()
+        check(L.nq_hits_from_arrays(p.ctypes.data, c.ctypes.data, g.ctypes.data, nq, C.byref(h)))
+        handles[i] = h
+    out = C.c_void_p()
+    try:
+        check(L.nq_hits_merge(handles, len(parts), C.byref(out)))
+        total = int(L.nq_hits_total(out))
+        ptr = np.ctypeslib.as_array(L.nq_hits_ptr(out), shape=(nq + 1,)).copy()
+        if total:
+            counts = np.ctypeslib.as_array(L.nq_hits_counts(out), shape=(total,)).copy()
+            gids = np.ctypeslib.as_array(L.nq_hits_gids(out), shape=(total,)).copy()
+        else:
+            counts, gids = np.zeros(0, np.uint32), np.zeros(0, np.uint32)
+    finally:
+        for h in handles:
+            L.nq_hits_free(h)
+        if out:
+            L.nq_hits_free(out)
+    return ptr, counts, gids

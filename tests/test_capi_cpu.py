@@ -121,3 +121,61 @@ def test_shard_range_and_hits_merge_host_side(capi):
     for s in range(shards):
         L.nq_hits_free(handles[s])
     L.nq_hits_free(out)
+
+
+def test_packer_wire_format_matches_the_character_rules(capi):
+    """K1 host half (pack.cpp): codes / `other` masks / seed rewriting against a plain numpy statement
+    of nuc2int, nuc2intrc and str2numstrand (niqki_index.cpp:114-123, 211-221, 255-273) — random
+    records with lower case, N runs and foreign bytes inside and outside the seeds, record
+    boundaries at every alignment, AVX2 and scalar tails."""
+    L = capi.lib()
+    rng = np.random.default_rng(11)
+    alphabet = np.frombuffer(b"ACGTACGTACGTACGTacgtNnRY*-\x00\xff", np.uint8)
+    for K in (31, 21, 5):
+        lens = [0, 1, K - 2, K - 1, K, K + 1, 47, 512, 513, 1000, 4097, 65536 + 13, 300_001]
+        recs = []
+        for i, n in enumerate(lens):
+            r = rng.choice(alphabet[:4], size=n)
+            dirty = rng.random(n) < (0.0, 0.02, 0.3)[i % 3]
+            r[dirty] = rng.choice(alphabet, size=int(dirty.sum()))
+            recs.append(r.astype(np.uint8))
+        bases = np.concatenate(recs)
+        offs = np.zeros(len(recs) + 1, np.uint64)
+        offs[1:] = np.cumsum([len(r) for r in recs])
+        words, blocks = C.c_uint64(), C.c_uint64()
+        capi.check(L.nq_pack_sizes(int(offs[-1]), C.byref(words), C.byref(blocks)))
+        codes = np.full(words.value, 0xDEADBEEF, np.uint32)
+        blk = np.full(blocks.value, 7, np.uint32)
+        pool = np.full(blocks.value * 32, 0xABCD, np.uint16)
+        used = C.c_uint64()
+        for threads in (1, 5):
+            capi.check(L.nq_pack_sequences(bases.ctypes.data, offs.ctypes.data, len(recs), K, codes.ctypes.data, blk.ctypes.data,
+                                           pool.ctypes.data, blocks.value, C.byref(used), threads))
+            # expected per-base forward code / other flag with the seed rule applied
+            fw = np.zeros(256, np.uint8); fw[ord("C")] = 1; fw[ord("G")] = 2; fw[ord("T")] = 3
+            ok = np.zeros(256, bool); ok[[ord(c) for c in "ACGT"]] = True
+            seedc = np.full(256, 4, np.uint8)
+            for j, c in enumerate("ACGT"):
+                seedc[ord(c)] = j; seedc[ord(c.lower())] = j
+            exp_code = fw[bases].copy(); exp_other = ~ok[bases]
+            for r in range(len(recs)):
+                e0, n = int(offs[r]), len(recs[r])
+                ns = min(n, K - 1)
+                sc = seedc[bases[e0:e0 + ns]]
+                exp_code[e0:e0 + ns] = sc if (sc < 4).all() else 0
+                exp_other[e0:e0 + ns] = False
+            lead = 512
+            total = words.value * 16
+            stream_code = np.zeros(total, np.uint8); stream_other = np.zeros(total, bool)
+            stream_code[lead:lead + len(bases)] = exp_code; stream_other[lead:lead + len(bases)] = exp_other
+            got_code = ((codes[:, None] >> (2 * np.arange(16, dtype=np.uint32))[None, :]) & 3).astype(np.uint8).ravel()
+            assert np.array_equal(got_code, stream_code), (K, threads)
+            exp_words = (stream_other.reshape(-1, 16) * (1 << np.arange(16))[None, :]).sum(1).astype(np.uint16)
+            for b in range(blocks.value):
+                w = exp_words[b * 32:(b + 1) * 32]
+                if blk[b] == 0xFFFFFFFF:
+                    assert not w.any(), (K, b)
+                else:
+                    assert blk[b] < used.value
+                    slot = pool[blk[b] * 32:blk[b] * 32 + 32]
+                    assert np.array_equal(slot[:len(w)], w), (K, b)

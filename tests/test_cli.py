@@ -180,3 +180,53 @@ def test_cli_multi_record_files_are_merged(tmp_path):
     rows = gunzip(tmp_path / "m.gz").decode().splitlines()
     assert rows[1].split("\t")[1:3] == ["1", "%g" % (shared / 256)]
     assert rows[2].split("\t")[1:3] == ["%g" % (shared / 256), "1"]
+
+
+def _device_count():
+    import ctypes as C
+
+    import niqki_b200
+
+    n = C.c_int(0)
+    return n.value if niqki_b200.lib().nq_device_count(C.byref(n)) == 0 else 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 3, 4, 8])
+def test_cli_sharded_over_gpus_is_byte_equal(c1_dir, small_dir, tmp_path, gpus):
+    """--gpus N (index sharded by genome id, queries all-gathered over NCCL, per-shard hits merged on
+    the host, --matrix tiled over the devices, dump concatenated in shard order): every output byte
+    equals the single-GPU / reference output.  Needs N visible devices (gpurun --gpus N)."""
+    if _device_count() < gpus:
+        pytest.skip(f"needs {gpus} CUDA devices")
+    g = ["--gpus", str(gpus)]
+    d, z = c1_dir
+    run_cli(g + ["-M", "file_of_file.txt", "-O", f"m{gpus}.gz"], d)
+    assert gunzip(d / f"m{gpus}.gz") == bytes(z["cli_matrix_text"])
+    run_cli(g + ["-I", "file_of_file.txt", "-Q", "file_of_file.txt", "-P", "-O", f"q{gpus}.gz"], d)
+    assert gunzip(d / f"q{gpus}.gz") == bytes(z["cli_query_text"])
+    d, z = small_dir
+    ps = json.loads(str(z["params"]))
+    flags = g + ["-K", str(ps["K"]), "-S", str(ps["S"]), "-W", str(ps["W"]), "-H", str(ps["H"]), "-J", str(ps["J"])]
+    run_cli(flags + ["-I", "fof.txt", "-Q", "qfof.txt", "-O", f"pretty{gpus}.gz", "-D", f"dump{gpus}.gz"], d)
+    assert gunzip(d / f"pretty{gpus}.gz") == bytes(z["pretty"])
+    dump = gunzip(d / f"dump{gpus}.gz")
+    assert hashlib.md5(dump).hexdigest() == str(z["dump_md5"])
+    run_cli(flags + ["-M", "fof.txt", "-O", f"matrix{gpus}.gz"], d)
+    assert gunzip(d / f"matrix{gpus}.gz") == bytes(z["matrix_text"])
+    run_cli(g + ["-L", f"dump{gpus}.gz", "-Q", "qfof.txt", "-O", f"loaded{gpus}.gz"], d)
+    assert gunzip(d / f"loaded{gpus}.gz") == bytes(z["pretty"])
+    (d / "fof_a.txt").write_text("".join(f"entry{i}\n" for i in range(30)))
+    (d / "fof_b.txt").write_text("".join(f"entry{i}\n" for i in range(30, 48)))
+    run_cli(flags + ["-I", "fof_a.txt", "-D", f"dump_a{gpus}.gz", "-O", "x.gz"], d)
+    run_cli(g + ["-L", f"dump_a{gpus}.gz", "-I", "fof_b.txt", "-D", f"dump_ab{gpus}.gz", "-Q", "qfof.txt", "-O", f"loaded2{gpus}.gz"], d)
+    assert gunzip(d / f"dump_ab{gpus}.gz") == dump
+    assert gunzip(d / f"loaded2{gpus}.gz") == bytes(z["pretty"])
+    # lines mode: reads as entries, far more entries than devices
+    z = load_npz("cli_lines.npz")
+    (tmp_path / "reads.fa").write_bytes(z["reads_fa"].tobytes())
+    (tmp_path / "reads.fq").write_bytes(z["reads_fq"].tobytes())
+    (tmp_path / "queries.fa").write_bytes(z["queries_fa"].tobytes())
+    for name, args in json.loads(str(z["runs"])).items():
+        run_cli(g + args + ["-O", f"{name}.gz"], tmp_path)
+        assert gunzip(tmp_path / f"{name}.gz") == bytes(z[f"out_{name}"]), name

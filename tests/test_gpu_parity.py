@@ -614,3 +614,79 @@ def test_query_forms_at_realistic_list_lengths(nb, ctx, n, S, J, what):
         lo, hi = ptr2[r * 40], ptr2[(r + 1) * 40]
         assert np.array_equal(ptr2[r * 40:(r + 1) * 40 + 1] - lo, ohp), what
         assert np.array_equal(c2[lo:hi], oc) and np.array_equal(gid2[lo:hi], og), what
+
+
+# ---- K1: the 2-bit packed wire format of the host-buffer sketch calls ----------------------------
+@pytest.fixture()
+def packed_ctx(nb):
+    c = nb.Context(0)
+    c.set_host_packing(1, 3)   # every entry travels packed, three packer threads
+    yield c
+    c.close()
+
+
+def test_packed_path_golden_sketches(nb, packed_ctx):
+    """Every adversarial case of sketches.npz (lower case, N runs, foreign bytes in and out of the
+    seed, len around K, -G masks, K in {11, 21, 31}) through pack.cpp + sketch_scan_packed_kernel."""
+    z = load_npz("sketches.npz")
+    psets = json.loads(str(z["param_sets"]))
+    checked = 0
+    for pi, ps in enumerate(psets):
+        g = gpu_index(nb, packed_ctx, **ps)
+        names = [str(n) for n in z["names"] if f"sk_{pi}_{n}" in z.files]
+        sks, flags = g.sketch_many([z["seq_" + n] for n in names])
+        for i, n in enumerate(names):
+            assert np.array_equal(sks[i], z[f"sk_{pi}_{n}"]), (ps, n)
+            checked += 1
+    assert checked > 100
+
+
+def test_packed_path_random_and_long_vs_oracle(nb, packed_ctx):
+    rng = np.random.default_rng(17)
+    alpha = b"ACGTNacgtRYK-"
+    pr = np.array([.22, .22, .22, .22, .03, .02, .02, .02, .01, .005, .005, .005, .005])
+    pr /= pr.sum()
+    for ps in [dict(K=31, S=8, W=12, H=4), dict(K=21, S=10, W=12, H=4), dict(K=13, S=6, W=8, H=3),
+               dict(K=31, S=12, W=12, H=4, genome_size=1000), dict(K=16, S=7, W=10, H=4), dict(K=17, S=7, W=10, H=4),
+               dict(K=11, S=4, W=6, H=2), dict(K=31, S=11, W=12, H=4)]:
+        o = oracle(**ps)
+        g = gpu_index(nb, packed_ctx, **ps)
+        seqs = []
+        while len(seqs) < 40:
+            s = rng.choice(np.frombuffer(alpha, np.uint8), size=int(rng.integers(ps["K"] + 1, 3000)), p=pr)
+            if o.compute_sketch(s, max_passes=100000)[1] >= 0:
+                seqs.append(s)
+        seqs += [b"ACGT" * 3, b"", b"A" * ps["K"]]
+        sks, flags = g.sketch_many(seqs)
+        assert np.array_equal(sks, o.sketch_many(seqs)), ps
+        assert list(flags[-3:]) == [1, 1, 1] and not flags[:-3].any()
+    # long entries: spans cut at 1024-base boundaries, 1024-thread CTAs, word-aligned thread runs
+    o = oracle(K=31, S=12, W=12, H=4)
+    g = gpu_index(nb, packed_ctx, K=31, S=12, W=12, H=4)
+    seqs = [random_dna(rng, 3_000_000), random_dna(rng, 70_001), random_dna(rng, 40), random_dna(rng, 1_000_003, b"ACGTN"),
+            random_dna(rng, 500_000, b"ACGTacgtN")]
+    sks, flags = g.sketch_many(seqs)
+    assert np.array_equal(sks, o.sketch_many(seqs))
+    # S > 15: global sketch behind the coarse filter, generic K
+    for S, W, H, K in [(16, 12, 4, 31), (17, 9, 3, 21)]:
+        o = oracle(K=K, S=S, W=W, H=H)
+        g = gpu_index(nb, packed_ctx, K=K, S=S, W=W, H=H)
+        seqs = [random_dna(rng, 1_500_000), random_dna(rng, 300_000, b"ACGTN")]
+        sks, _ = g.sketch_many(seqs)
+        assert np.array_equal(sks, o.sketch_many(seqs))
+
+
+def test_packed_and_character_paths_agree_on_a_multi_batch_call(nb, ctx, packed_ctx):
+    """More than one 512 MB batch through both host paths (double-buffered staging), equal sketches."""
+    rng = np.random.default_rng(23)
+    g0 = gpu_index(nb, ctx, K=31, S=10, W=12, H=4)
+    g1 = gpu_index(nb, packed_ctx, K=31, S=10, W=12, H=4)
+    one = random_dna(rng, 4_000_000, b"ACGTN")
+    seqs = [np.roll(np.frombuffer(one, np.uint8), 1000 * i) for i in range(300)]   # 1.2 GB
+    ctx.set_host_packing(0, 0)
+    a, _ = g0.sketch_many(seqs)
+    ctx.set_host_packing(-1, 0)
+    b, _ = g1.sketch_many(seqs)
+    assert np.array_equal(a, b)
+    o = oracle(K=31, S=10, W=12, H=4)
+    assert np.array_equal(a[:2], o.sketch_many(seqs[:2]))

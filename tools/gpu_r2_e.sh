@@ -1,0 +1,36 @@
+#!/bin/bash
+# round 2: fixed-round slab count kernel with leader-driven prefetch; packed sketch path first contact
+mkdir -p gpurun_out
+( time timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q ) > gpurun_out/r2e_pytest.log 2>&1
+tail -5 gpurun_out/r2e_pytest.log
+export NIQKI_B200_LIB=$PWD/niqki_b200/lib_tuning/libniqki_b200.so
+run() {  # name, env...
+  name=$1; shift
+  env "$@" timeout 300 python bench.py --workload q100k --genomes ${G:-10000} --queries ${Q:-1000} --steps 5 --warmup 3 > gpurun_out/r2e_$name.json 2> gpurun_out/r2e_$name.err
+}
+run base X=1
+run nocount NQ_QUERY_EXP=1
+run nogather NQ_QUERY_EXP=2
+run neither NQ_QUERY_EXP=3
+run nopf NQ_QUERY_PF_AHEAD=0
+run pf3 NQ_QUERY_PF_AHEAD=3
+run pf4 NQ_QUERY_PF_AHEAD=4
+run nrf4 NQ_SLAB_NRF=4
+run nrf0 NQ_SLAB_NRF=0
+G=12500 Q=10000 run base_c3 X=1
+G=12500 Q=10000 run nopf_c3 NQ_QUERY_PF_AHEAD=0
+G=12500 Q=10000 run pf4_c3 NQ_QUERY_PF_AHEAD=4
+G=12500 Q=10000 run nrf3_c3 NQ_SLAB_NRF=3
+G=25000 Q=10000 run base_25k X=1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"query_slab|slab_resolve" -c 2 -o gpurun_out/r2e_slab \
+  python bench.py --workload q100k --genomes 10000 --queries 1000 --steps 1 --warmup 0 > gpurun_out/r2e_ncu.log 2>&1
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r2e_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        r=d.get('roofline')
+        print(f, 'ms',round(d['ms_per_step'],4),'frac',r.get('frac'), 'kern ms', r.get('ms_per_launch'))
+    except Exception as e:
+        print(f,'ERR',e, open(f.replace('.json','.err')).read()[-300:])
+PY
