@@ -138,8 +138,11 @@ extern "C" int nq_ctx_destroy(nq_ctx* ctx) {
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+  if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+  if (ctx->ring_wrap) cudaEventDestroy(ctx->ring_wrap);
   for (auto& s : ctx->slot) {
     cudaFree(s.d_bases); cudaFree(s.d_sk); cudaFree(s.d_flags);
+    cudaFreeHost(s.h_flags);
     cudaFree(s.d_codes); cudaFree(s.d_blk); cudaFree(s.d_pool);
     cudaFreeHost(s.h_codes); cudaFreeHost(s.h_blk); cudaFreeHost(s.h_pool);
     if (s.h2d) cudaEventDestroy(s.h2d);
@@ -147,6 +150,35 @@ extern "C" int nq_ctx_destroy(nq_ctx* ctx) {
     if (s.d2h) cudaEventDestroy(s.d2h);
   }
   delete ctx;
+  return NQ_OK;
+}
+
+int nq_upload_small(nq_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (bytes == 0) return NQ_OK;
+  constexpr size_t kRing = 16u << 20;
+  if (bytes > kRing / 4) {  // large tables: plain copy (synchronises the stream when the source is pageable)
+    NQ_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NQ_OK;
+  }
+  if (!ctx->h_ring) {
+    NQ_CUDA(cudaMallocHost((void**)&ctx->h_ring, kRing));
+    ctx->ring_cap = kRing;
+    NQ_CUDA(cudaEventCreateWithFlags(&ctx->ring_wrap, cudaEventDisableTiming));
+    NQ_CUDA(cudaEventRecord(ctx->ring_wrap, ctx->stream));
+  }
+  const size_t need = (bytes + 255) & ~(size_t)255;
+  if (ctx->ring_at + need > ctx->ring_cap) {
+    // wrap: everything queued from the ring's previous lap must have been copied before it is overwritten.
+    // The half-way mark is awaited, so the host only ever waits for uploads queued half a ring ago.
+    NQ_CUDA(cudaEventRecord(ctx->ring_wrap, ctx->stream));
+    NQ_CUDA(cudaEventSynchronize(ctx->ring_wrap));
+    ctx->ring_at = 0;
+  }
+  char* slot = ctx->h_ring + ctx->ring_at;
+  memcpy(slot, h_src, bytes);
+  ctx->ring_at += need;
+  NQ_CUDA(cudaMemcpyAsync(d_dst, slot, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return NQ_OK;
 }
 
@@ -208,12 +240,14 @@ extern "C" void nq_host_free(void* p) {
 
 extern "C" int nq_sketch_batch_device(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint64_t bases_capacity,
                                       const uint64_t* offsets, uint64_t n, int32_t* d_sketches, uint32_t* d_flags) {
+  NQ_RANGE();
   if (!ctx || !offsets || (n && (!d_bases || !d_sketches))) return nq_set_error(NQ_ERR_INVALID, "null argument");
   NQ_CUDA(cudaSetDevice(ctx->device));
   return nq_launch_sketch(ctx, p, d_bases, bases_capacity, offsets, n, nullptr, n, d_sketches, d_flags);
 }
 
 extern "C" int nq_densify_device(nq_ctx* ctx, const nq_params* p, int32_t* d_sketches, uint64_t n, uint32_t* d_flags) {
+  NQ_RANGE();
   if (!ctx || (n && !d_sketches)) return nq_set_error(NQ_ERR_INVALID, "null argument");
   NQ_CUDA(cudaSetDevice(ctx->device));
   return nq_launch_densify(ctx, p, d_sketches, n, d_flags);
@@ -232,7 +266,10 @@ static int sketch_records_impl(nq_ctx* ctx, const nq_params* p, const char* base
   if (!rec_entry) n_entries = n_rec;
   if (n_entries == 0) return NQ_OK;
   const uint64_t F = p->F;
-  const uint64_t max_bases = 512ull << 20, max_cells = (1ull << 30) / 4;  // per batch: 512 MB in, 1 GB out
+  // long entries may travel packed (below): smaller batches, so that packing one overlaps the copy of another
+  const bool long_entries = n_rec && (offsets[n_rec] - offsets[0]) / n_rec >= 4096;
+  const bool packed = ctx->pack_mode == 1 || (ctx->pack_mode != 0 && long_entries);
+  const uint64_t max_bases = packed ? 192ull << 20 : 512ull << 20, max_cells = (1ull << 30) / 4;  // per batch; <= 1 GB of sketches out
   // first record of every entry (entries without records are legal: they stay empty and are flagged)
   std::vector<uint64_t> first(n_entries + 1, n_rec);
   if (rec_entry) {
@@ -268,16 +305,17 @@ static int sketch_records_impl(nq_ctx* ctx, const nq_params* p, const char* base
     cap_bases = std::max(cap_bases, offsets[first[cut[b + 1]]] - offsets[first[cut[b]]]);
     cap_entries = std::max(cap_entries, cut[b + 1] - cut[b]);
   }
-  // K1: long entries travel as 2 bits per base (packed on the host by pack.cpp while the previous
-  // batch is on the device); short reads keep the character form (their kernel fuses densification
-  // and the per-record seed fix-up of the packer would dominate)
-  const uint64_t total_bytes = offsets[first[n_entries]] - offsets[first[0]];
-  const bool packed = ctx->pack_mode == 1 || (ctx->pack_mode != 0 && n_rec && total_bytes / n_rec >= 4096);
+  // K1: long entries travel as 2 bits per base, packed on the host (pack.cpp) while earlier batches are on the
+  // link and the device.  Short reads keep the character form: their kernel fuses densification, and the
+  // per-record seed fix-up of the packer would dominate.  (Sending a share of the batches as characters, so
+  // that the link works while the cores pack, was built and measured on a 16-core host: 68-73 Gbases/s
+  // against 83 with everything packed — the DMA reads and the packer's reads share the host's memory
+  // bandwidth — and removed.)
   const uint64_t cap_words = nq_pack_words(cap_bases), cap_blocks = nq_pack_blocks(cap_bases);
   cap_bases = (cap_bases + 15 + 16) & ~15ull;
   int st = NQ_OK;
   cudaError_t e = cudaSuccess;
-  const int nslots = cut.size() > 2 ? 2 : 1;
+  const int nslots = cut.size() > 3 && packed ? 3 : cut.size() > 2 ? 2 : 1;
   for (int i = 0; i < nslots && e == cudaSuccess; ++i) {
     nq_ctx::Slot& s = ctx->slot[i];
     if (!s.h2d) {
@@ -293,7 +331,6 @@ static int sketch_records_impl(nq_ctx* ctx, const nq_params* p, const char* base
           (e = cudaMalloc((void**)&s.d_pool, cap_blocks * 64)) != cudaSuccess || (e = cudaMallocHost((void**)&s.h_codes, cap_words * 4)) != cudaSuccess ||
           (e = cudaMallocHost((void**)&s.h_blk, cap_blocks * 4)) != cudaSuccess || (e = cudaMallocHost((void**)&s.h_pool, cap_blocks * 64)) != cudaSuccess)
         break;
-      s.dense.resize(cap_words);
       s.cap_words = cap_words;
     }
     if (!packed && s.cap_bases < cap_bases) {
@@ -308,20 +345,28 @@ static int sketch_records_impl(nq_ctx* ctx, const nq_params* p, const char* base
     }
     if (s.cap_entries < cap_entries) {
       cudaFree(s.d_flags); s.d_flags = nullptr; s.cap_entries = 0;
-      if ((e = cudaMalloc((void**)&s.d_flags, cap_entries * 4)) != cudaSuccess) break;
+      cudaFreeHost(s.h_flags); s.h_flags = nullptr;
+      if ((e = cudaMalloc((void**)&s.d_flags, cap_entries * 4)) != cudaSuccess ||
+          (e = cudaMallocHost((void**)&s.h_flags, cap_entries * 4)) != cudaSuccess)
+        break;
       s.cap_entries = cap_entries;
     }
+    s.flags_n = 0;
   }
   if (e != cudaSuccess) st = nq_set_error(NQ_ERR_CUDA, "sketch batch allocation failed: %s", cudaGetErrorString(e));
-  std::vector<uint64_t> local_off[2];
-  std::vector<uint32_t> local_ent[2];
+  std::vector<uint64_t> local_off[3];
+  std::vector<uint32_t> local_ent[3];
   for (size_t b = 0; st == NQ_OK && b + 1 < cut.size(); ++b) {
     nq_ctx::Slot& s = ctx->slot[b % nslots];
     std::vector<uint64_t>& loff = local_off[b % nslots];
     std::vector<uint32_t>& lent = local_ent[b % nslots];
     const uint64_t e0 = cut[b], e1 = cut[b + 1], nb = e1 - e0;
     const uint64_t r0 = first[e0], r1 = first[e1], nr = r1 - r0, base0 = offsets[r0], nbytes = offsets[r1] - base0;
-    if (b >= (size_t)nslots) cudaEventSynchronize(s.d2h);  // the slot's previous results are out
+    if (b >= (size_t)nslots) {
+      cudaEventSynchronize(s.d2h);  // the slot's previous results are out
+      if (flags && s.flags_n) memcpy(flags + s.flags_e0, s.h_flags, s.flags_n * 4);
+      s.flags_n = 0;
+    }
     loff.resize(nr + 1);
     for (uint64_t i = 0; i <= nr; ++i) loff[i] = offsets[r0 + i] - base0;
     if (rec_entry) {
@@ -329,12 +374,12 @@ static int sketch_records_impl(nq_ctx* ctx, const nq_params* p, const char* base
       for (uint64_t i = 0; i < nr; ++i) lent[i] = rec_entry[r0 + i] - (uint32_t)e0;
     }
     int32_t* d_out = out_on_device ? sketches + e0 * F : s.d_sk;
-    if (packed) {
+    const unsigned nt = ctx->host_threads ? ctx->host_threads : std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    const bool as_packed = packed;
+    if (as_packed) {
       if (b >= (size_t)nslots) cudaEventSynchronize(s.h2d);  // the staging buffers have left for the device
-      unsigned nt = ctx->host_threads ? ctx->host_threads : std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
       const uint64_t words = nq_pack_words(nbytes), blocks = nq_pack_blocks(nbytes);
-      const uint64_t used = nq_pack_host(bases + base0, nbytes, loff.data(), nr, p->K, s.h_codes, s.h_blk, s.h_pool, cap_blocks,
-                                         s.dense.data(), nt);
+      const uint64_t used = nq_pack_host(bases + base0, nbytes, loff.data(), nr, p->K, s.h_codes, s.h_blk, s.h_pool, cap_blocks, nt);
       if (used == ~0ull) { st = nq_set_error(NQ_ERR_INVALID, "packer: mask pool overflow"); break; }
       if ((e = cudaMemcpyAsync(s.d_codes, s.h_codes, words * 4, cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess ||
           (e = cudaMemcpyAsync(s.d_blk, s.h_blk, blocks * 4, cudaMemcpyHostToDevice, ctx->copy_stream)) != cudaSuccess ||
@@ -348,6 +393,7 @@ static int sketch_records_impl(nq_ctx* ctx, const nq_params* p, const char* base
       st = nq_launch_sketch_packed(ctx, p, s.d_codes, s.d_blk, s.d_pool, loff.data(), nr, rec_entry ? lent.data() : nullptr, nb,
                                    d_out, s.d_flags);
     } else {
+      if (b >= (size_t)nslots) cudaEventSynchronize(s.done);  // the slot's character buffer is no longer read
       if (nbytes) e = cudaMemcpyAsync(s.d_bases, bases + base0, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream);
       if (e != cudaSuccess) { st = nq_set_error(NQ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
       ctx->h2d_bytes += nbytes;
@@ -360,8 +406,10 @@ static int sketch_records_impl(nq_ctx* ctx, const nq_params* p, const char* base
     cudaEventRecord(s.done, ctx->stream);
     cudaStreamWaitEvent(ctx->d2h_stream, s.done, 0);
     if (!out_on_device) e = cudaMemcpyAsync(sketches + e0 * F, s.d_sk, nb * F * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
-    if (e == cudaSuccess && flags)
-      e = cudaMemcpyAsync(flags + e0, s.d_flags, nb * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+    if (e == cudaSuccess && flags) {
+      e = cudaMemcpyAsync(s.h_flags, s.d_flags, nb * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+      s.flags_e0 = e0; s.flags_n = nb;
+    }
     if (e != cudaSuccess) { st = nq_set_error(NQ_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); break; }
     cudaEventRecord(s.d2h, ctx->d2h_stream);
   }
@@ -371,17 +419,24 @@ static int sketch_records_impl(nq_ctx* ctx, const nq_params* p, const char* base
     st = nq_set_error(NQ_ERR_CUDA, "sketch batch failed: %s", cudaGetErrorString(e));
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess && st == NQ_OK)
     st = nq_set_error(NQ_ERR_CUDA, "sketch batch failed: %s", cudaGetErrorString(e));
+  for (int i = 0; i < nslots; ++i) {
+    nq_ctx::Slot& s = ctx->slot[i];
+    if (flags && s.flags_n && st == NQ_OK) memcpy(flags + s.flags_e0, s.h_flags, s.flags_n * 4);
+    s.flags_n = 0;
+  }
   return st;
 }
 
 extern "C" int nq_sketch_batch(nq_ctx* ctx, const nq_params* p, const char* bases, const uint64_t* offsets, uint64_t n,
                                int32_t* sketches, uint32_t* flags) {
+  NQ_RANGE();
   return sketch_records_impl(ctx, p, bases, offsets, n, nullptr, n, sketches, flags, false);
 }
 
 extern "C" int nq_sketch_records(nq_ctx* ctx, const nq_params* p, const char* bases, const uint64_t* rec_offsets,
                                  uint64_t n_records, const uint32_t* rec_entry, uint64_t n_entries, int32_t* sketches,
                                  uint32_t* flags, int sketches_on_device) {
+  NQ_RANGE();
   return sketch_records_impl(ctx, p, bases, rec_offsets, n_records, rec_entry, n_entries, sketches, flags,
                              sketches_on_device != 0);
 }
@@ -415,6 +470,7 @@ extern "C" int nq_device_copy(nq_ctx* ctx, void* dst, const void* src, size_t by
 
 extern "C" int nq_index_build_device(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketches, uint64_t n,
                                      uint32_t gid_base, nq_index** out) {
+  NQ_RANGE();
   if (!ctx || !d_sketches || !out) return nq_set_error(NQ_ERR_INVALID, "null argument");
   NQ_CUDA(cudaSetDevice(ctx->device));
   return nq_index_build_impl(ctx, p, d_sketches, n, gid_base, out);
@@ -422,6 +478,7 @@ extern "C" int nq_index_build_device(nq_ctx* ctx, const nq_params* p, const int3
 
 extern "C" int nq_index_build(nq_ctx* ctx, const nq_params* p, const int32_t* sketches, uint64_t n, uint32_t gid_base,
                               nq_index** out) {
+  NQ_RANGE();
   if (!ctx || !sketches || !out) return nq_set_error(NQ_ERR_INVALID, "null argument");
   NQ_TRY(nq_params_check(p));
   NQ_CUDA(cudaSetDevice(ctx->device));
@@ -437,12 +494,14 @@ extern "C" int nq_index_build(nq_ctx* ctx, const nq_params* p, const int32_t* sk
 
 extern "C" int nq_query_batch_device(nq_index* ix, const int32_t* d_sketches, uint64_t nq, uint32_t min_score,
                                      nq_hits** out) {
+  NQ_RANGE();
   if (!ix || (nq && !d_sketches)) return nq_set_error(NQ_ERR_INVALID, "null argument");
   NQ_CUDA(cudaSetDevice(ix->ctx->device));
   return nq_query_impl(ix, d_sketches, nq, min_score, out);
 }
 
 extern "C" int nq_query_batch(nq_index* ix, const int32_t* sketches, uint64_t nq, uint32_t min_score, nq_hits** out) {
+  NQ_RANGE();
   if (!ix || !out || (nq && !sketches)) return nq_set_error(NQ_ERR_INVALID, "null argument");
   nq_ctx* ctx = ix->ctx;
   NQ_CUDA(cudaSetDevice(ctx->device));
@@ -463,18 +522,21 @@ extern "C" const uint32_t* nq_hits_gids(const nq_hits* h) { return h ? h->gids.d
 extern "C" void nq_hits_free(nq_hits* h) { delete h; }
 
 extern "C" int nq_matrix_rows(nq_index* ix, uint32_t row_begin, uint32_t row_end, int wrap16, uint32_t* counts) {
+  NQ_RANGE();
   if (!ix) return nq_set_error(NQ_ERR_INVALID, "null index");
   NQ_CUDA(cudaSetDevice(ix->ctx->device));
   return nq_matrix_impl(ix, row_begin, row_end, wrap16, counts);
 }
 
 extern "C" int nq_index_sketches_device(nq_index* ix, uint32_t row_begin, uint32_t row_end, int32_t* d_sketches) {
+  NQ_RANGE();
   if (!ix) return nq_set_error(NQ_ERR_INVALID, "null index");
   NQ_CUDA(cudaSetDevice(ix->ctx->device));
   return nq_index_sketches_impl(ix, row_begin, row_end, d_sketches);
 }
 
 extern "C" int nq_matrix_tile(nq_index* ix, const int32_t* d_row_sketches, uint32_t nrows, int wrap16, uint32_t* counts) {
+  NQ_RANGE();
   if (!ix) return nq_set_error(NQ_ERR_INVALID, "null index");
   NQ_CUDA(cudaSetDevice(ix->ctx->device));
   return nq_matrix_tile_impl(ix, d_row_sketches, nrows, wrap16, counts);
@@ -517,13 +579,13 @@ extern "C" int nq_pack_sizes(uint64_t nbytes, uint64_t* words, uint64_t* blocks)
 
 extern "C" int nq_pack_sequences(const char* bases, const uint64_t* rec_offsets, uint64_t n_records, uint32_t K, uint32_t* codes,
                                  uint32_t* blk, uint16_t* pool, uint64_t pool_slots, uint64_t* pool_used, unsigned threads) {
+  NQ_RANGE();
   if (!rec_offsets || !codes || !blk || (n_records && !bases)) return nq_set_error(NQ_ERR_INVALID, "null argument");
   if (K < 2 || K > 31) return nq_set_error(NQ_ERR_INVALID, "K=%u outside [2,31]", K);
   const uint64_t nbytes = rec_offsets[n_records] - rec_offsets[0];
-  std::vector<uint16_t> dense(nq_pack_words(nbytes));
   if (threads == 0) threads = std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
   const uint64_t used = nq_pack_host(bases + rec_offsets[0], nbytes, rec_offsets, n_records, K, codes, blk, pool, pool ? pool_slots : 0,
-                                     dense.data(), threads);
+                                     threads);
   if (used == ~0ull) return nq_set_error(NQ_ERR_OVERFLOW, "mask pool too small (%llu slots)", (unsigned long long)pool_slots);
   if (pool_used) *pool_used = used;
   return NQ_OK;
@@ -532,6 +594,7 @@ extern "C" int nq_pack_sequences(const char* bases, const uint64_t* rec_offsets,
 extern "C" int nq_sketch_batch_packed_device(nq_ctx* ctx, const nq_params* p, const uint32_t* d_codes, const uint32_t* d_blk,
                                              const uint16_t* d_pool, const uint64_t* offsets, uint64_t n, int32_t* d_sketches,
                                              uint32_t* d_flags) {
+  NQ_RANGE();
   if (!ctx || !offsets || (n && (!d_codes || !d_blk || !d_sketches))) return nq_set_error(NQ_ERR_INVALID, "null argument");
   if (n && offsets[0] != 0) return nq_set_error(NQ_ERR_INVALID, "offsets of a packed batch start at 0");
   NQ_CUDA(cudaSetDevice(ctx->device));

@@ -207,6 +207,7 @@ static int wire_reserve(nq_comm* c, size_t cells) {
 }
 
 extern "C" int nq_allgather_sketches(nq_comm* c, const nq_params* p, const int32_t* d_local, uint64_t n_local, int32_t* d_all) {
+  NQ_RANGE();
   if (!c || !p || (n_local && (!d_local || !d_all))) return nq_set_error(NQ_ERR_INVALID, "null argument");
   if (n_local == 0) return NQ_OK;
   nq_ctx* ctx = c->ctx;
@@ -235,6 +236,7 @@ extern "C" int nq_allgather_sketches(nq_comm* c, const nq_params* p, const int32
 }
 
 extern "C" int nq_bcast_sketches(nq_comm* c, const nq_params* p, int32_t* d_sketches, uint64_t n, int root) {
+  NQ_RANGE();
   if (!c || !p || (n && !d_sketches) || root < 0 || root >= c->nranks) return nq_set_error(NQ_ERR_INVALID, "bad broadcast arguments");
   if (n == 0 || c->nranks == 1) return NQ_OK;
   nq_ctx* ctx = c->ctx;
@@ -260,6 +262,7 @@ extern "C" int nq_bcast_sketches(nq_comm* c, const nq_params* p, int32_t* d_sket
 
 // Host merge of per-shard results of the SAME query batch (:685 ordering).
 extern "C" int nq_hits_merge(const nq_hits* const* parts, int nparts, nq_hits** out) {
+  NQ_RANGE();
   if (!parts || !out || nparts < 1) return nq_set_error(NQ_ERR_INVALID, "bad merge arguments");
   for (int s = 0; s < nparts; ++s)
     if (!parts[s] || parts[s]->ptr.size() != parts[0]->ptr.size())

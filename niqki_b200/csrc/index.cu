@@ -542,7 +542,10 @@ static cudaError_t launch_cell_sort(nq_ctx* ctx, const uint16_t* d_fpT, uint32_t
                                     unsigned long long* d_total) {
   const uint32_t range = (uint32_t)ix->p.range, F = ix->p.F;
   const size_t per_warp = (size_t)range * sizeof(IT);
-  const uint32_t nw = 8;
+  // warps per CTA: as many as their 2^W counters fit (8 at W <= 12, 1 at W = 15 with u32 ids)
+  uint32_t nw = 8;
+  while (nw > 1 && per_warp * nw + 1024 > ctx->smem_optin) nw >>= 1;
+  if (per_warp * nw + 1024 > ctx->smem_optin) return cudaErrorInvalidValue;
   const size_t smem = per_warp * nw;
   cudaError_t e = cudaFuncSetAttribute(cell_sort_kernel<IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -567,7 +570,9 @@ static cudaError_t launch_chunked_sort(nq_ctx* ctx, const uint16_t* d_fpT, uint3
   // worth it only when one warp per cell cannot fill the SMs and there is more than one chunk
   if (ix->elem != 4 || chunks < 2 || F >= (uint32_t)ctx->sm_count * 16 || tasks * range * 4 > (8ull << 30))
     return cudaErrorInvalidValue;
-  const uint32_t nw = 8;
+  uint32_t nw = 8;
+  while (nw > 1 && (size_t)range * 4 * nw + 1024 > ctx->smem_optin) nw >>= 1;
+  if ((size_t)range * 4 * nw + 1024 > ctx->smem_optin) return cudaErrorInvalidValue;
   const size_t smem = (size_t)range * 4 * nw;
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(chunk_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess ||
@@ -623,12 +628,11 @@ static void set_layout(nq_index* ix) {
 int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketches, uint64_t n64,
                         uint32_t gid_base, nq_index** out) {
   NQ_TRY(nq_params_check(p));
-  if (p->W > 15) return nq_set_error(NQ_ERR_UNSUPPORTED, "index build supports W <= 15 (got W=%u)", p->W);
+  if (p->W > 15)  // u16 fingerprint transpose and per-cell shared-memory counters; the reference takes any W + S < 32
+    return nq_set_error(NQ_ERR_UNSUPPORTED, "index build supports W <= 15 (got W=%u)", p->W);
   if (n64 == 0 || n64 > 0xFFFFFFF0ull || n64 + gid_base > 0xFFFFFFFFull)
     return nq_set_error(NQ_ERR_INVALID, "bad genome count %llu (gid_base %u)", (unsigned long long)n64, gid_base);
   const uint32_t n = (uint32_t)n64, F = p->F, range = (uint32_t)p->range;
-  if ((size_t)range * 4 * 8 > ctx->smem_optin)
-    return nq_set_error(NQ_ERR_UNSUPPORTED, "2^W counters do not fit in shared memory");
 
   nq_index* ix = new nq_index();
   ix->ctx = ctx; ix->p = *p; ix->n = n; ix->gid_base = gid_base;
@@ -663,6 +667,8 @@ int nq_index_build_impl(nq_ctx* ctx, const nq_params* p, const int32_t* d_sketch
   if (e == cudaErrorInvalidValue)  // u32 ids, or a cell that does not fit in shared memory: one warp per cell
     e = ix->elem == 2 ? launch_cell_sort<uint16_t>(ctx, d_fpT, n, n_pad, ix, d_total)
                       : launch_cell_sort<uint32_t>(ctx, d_fpT, n, n_pad, ix, d_total);
+  if (e == cudaErrorInvalidValue)
+    return fail(nq_set_error(NQ_ERR_UNSUPPORTED, "2^W = %u fingerprint counters of one cell do not fit in shared memory", range));
   if (e != cudaSuccess) return fail(nq_set_error(NQ_ERR_CUDA, "cell_sort launch failed: %s", cudaGetErrorString(e)));
   unsigned long long total = 0;
   if ((e = cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
@@ -742,6 +748,7 @@ static int export_t(nq_index* ix, uint32_t* list_sizes, uint32_t* gids) {
 }
 
 extern "C" int nq_index_export(nq_index* ix, uint32_t* list_sizes, uint32_t* gids, uint64_t gids_capacity) {
+  NQ_RANGE();
   if (!ix) return nq_set_error(NQ_ERR_INVALID, "null index");
   if (gids && gids_capacity < ix->n_postings)
     return nq_set_error(NQ_ERR_OVERFLOW, "gids capacity %llu < %llu postings", (unsigned long long)gids_capacity,
@@ -773,6 +780,9 @@ static int import_t(nq_index* ix, const uint32_t* list_sizes, const uint32_t* gi
           gp[run++] = (IT)(g - ix->gid_base);
         }
       }
+      // the reference's own dumps hold a list in the order its OpenMP threads appended; the
+      // split16 directory and the granule form rely on gid order, and no result depends on list order
+      if (run - begin > 1 && !std::is_sorted(gp + begin, gp + run)) std::sort(gp + begin, gp + run);
       r += sz;
       rowp[f] = DirEntry<IT>::make(begin, run);
     }
@@ -793,6 +803,7 @@ static int import_t(nq_index* ix, const uint32_t* list_sizes, const uint32_t* gi
 
 extern "C" int nq_index_import(nq_ctx* ctx, const nq_params* p, const uint32_t* list_sizes, const uint32_t* gids,
                                uint32_t n_genomes, uint32_t gid_base, nq_index** out) {
+  NQ_RANGE();
   NQ_TRY(nq_params_check(p));
   if (!ctx || !list_sizes || !gids || !out) return nq_set_error(NQ_ERR_INVALID, "null argument");
   if (n_genomes == 0) return nq_set_error(NQ_ERR_INVALID, "empty shard");

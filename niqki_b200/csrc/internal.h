@@ -22,13 +22,18 @@ struct nq_ctx {
     char* d_bases = nullptr; size_t cap_bases = 0;
     int32_t* d_sk = nullptr; size_t cap_cells = 0;
     uint32_t* d_flags = nullptr; size_t cap_entries = 0;
+    uint32_t* h_flags = nullptr;               // pinned landing buffer of the flags (the caller's array may be pageable:
+    uint64_t flags_e0 = 0, flags_n = 0;        // a direct copy would block the host until the batch is done)
     cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
     // 2-bit packed form of the batch (pack.cpp): pinned host staging + device copies
     uint32_t* h_codes = nullptr; uint32_t* d_codes = nullptr; size_t cap_words = 0;
     uint32_t* h_blk = nullptr; uint32_t* d_blk = nullptr;
     uint16_t* h_pool = nullptr; uint16_t* d_pool = nullptr;
-    std::vector<uint16_t> dense;  // host scratch of the packer
-  } slot[2];
+  } slot[3];
+  // pinned ring for small host -> device uploads (span tables, offsets) that must not stall the host:
+  // a copy from pageable memory would wait for the stream
+  char* h_ring = nullptr; size_t ring_cap = 0, ring_at = 0;
+  cudaEvent_t ring_wrap = nullptr;  // recorded when the write position wraps; awaited before the ring is reused
   unsigned host_threads = 0;  // packer threads (0 = hardware concurrency, capped)
   int pack_mode = -1;         // -1 auto (long entries travel packed), 0 never, 1 always
   int sm_count = 148;
@@ -88,7 +93,32 @@ inline void nq_dfree(nq_ctx* ctx, void* p) {
   if (p) cudaFreeAsync(p, ctx->stream);
 }
 
+// NVTX range around a C-ABI entry point (tracing): shows up in Nsight Systems / ncu --nvtx
+// timelines under the domain "niqki_b200"; a no-op when no tool is attached.
+#include <nvtx3/nvToolsExt.h>
+struct NqRange {
+  explicit NqRange(const char* name) { nvtxRangePushA(name); }
+  ~NqRange() { nvtxRangePop(); }
+  NqRange(const NqRange&) = delete;
+  NqRange& operator=(const NqRange&) = delete;
+};
+#define NQ_RANGE() NqRange _nq_range(__func__)
+
+// stream-ordered scratch that is returned on every path out of a function
+struct NqScratch {
+  nq_ctx* ctx;
+  void* p = nullptr;
+  explicit NqScratch(nq_ctx* c) : ctx(c) {}
+  NqScratch(const NqScratch&) = delete;
+  NqScratch& operator=(const NqScratch&) = delete;
+  ~NqScratch() { nq_dfree(ctx, p); }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
 int nq_params_check(const nq_params* p);
+// stream-ordered upload of a small host array through the context's pinned ring (capi.cu)
+int nq_upload_small(nq_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 
 // Measurement knobs (NQ_* environment variables) exist only in builds with -DNQ_TUNING; the
 // product library never lets the environment choose a kernel.

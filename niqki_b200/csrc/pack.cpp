@@ -17,8 +17,11 @@
 // The stream starts with kPackLead unused bases (the window of a record's first k-mer begins one
 // base early).
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -75,92 +78,189 @@ __attribute__((target("avx2,bmi2"))) inline void pack32_avx2(const uint8_t* s, u
 }
 #endif
 
-bool have_avx2() {
+// Helper threads that outlive a call: a batch is packed in ~2 ms, starting 15 threads for it costs as much.
+class Workers {
+ public:
+  static Workers& get() {
+    static Workers w;
+    return w;
+  }
+  // runs fn() on `extra` helper threads and on the caller; returns when all are done
+  void run(unsigned extra, const std::function<void()>& fn) {
+    std::lock_guard<std::mutex> one_call(call_);
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      while (threads_.size() < extra) threads_.emplace_back([this, i = threads_.size()] { loop(i); });
+      fn_ = &fn;
+      want_ = extra;
+      running_ = extra;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    fn();
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this] { return running_ == 0; });
+    fn_ = nullptr;
+  }
+  ~Workers() {
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+
+ private:
+  void loop(size_t me) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void()>* fn = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || (epoch_ != seen && me < want_); });
+        if (stop_) return;
+        seen = epoch_;
+        fn = fn_;
+      }
+      (*fn)();
+      std::unique_lock<std::mutex> lk(m_);
+      if (--running_ == 0) done_.notify_all();
+    }
+  }
+  std::mutex m_, call_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> threads_;
+  const std::function<void()>* fn_ = nullptr;
+  uint64_t epoch_ = 0;
+  unsigned want_ = 0, running_ = 0;
+  bool stop_ = false;
+};
+
+int simd_level() {  // 2: AVX-512BW + BMI2, 1: AVX2 + BMI2, 0: scalar
 #if defined(__x86_64__)
-  static const bool ok = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
-  return ok;
+  static const int lvl = (__builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("bmi2")) ? 2
+                         : (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2")) ? 1 : 0;
+  return lvl;
 #else
-  return false;
+  return 0;
 #endif
 }
 
 #if defined(__x86_64__)
-__attribute__((target("avx2,bmi2"))) void pack_range_avx2(const uint8_t* src, uint64_t w0, uint64_t w1, uint64_t nbytes,
-                                                          uint32_t* codes, uint16_t* other) {
-  // words w0..w1 of the SOURCE stream (word w = bytes 16w .. 16w+15); full 32-byte pairs with AVX2
-  uint64_t w = w0;
-  for (; w + 2 <= w1 && (w + 2) * 16 <= nbytes; w += 2) {
-    uint64_t c;
-    uint32_t o;
-    pack32_avx2(src + w * 16, c, o);
-    codes[w] = (uint32_t)c;
-    codes[w + 1] = (uint32_t)(c >> 32);
-    other[w] = (uint16_t)o;
-    other[w + 1] = (uint16_t)(o >> 16);
-  }
-  for (; w < w1; ++w) {
-    const uint64_t at = w * 16;
-    const uint32_t n = at >= nbytes ? 0u : (uint32_t)(nbytes - at < 16 ? nbytes - at : 16);
-    pack16_scalar(src + at, n, codes[w], other[w]);
-  }
+// 64 bases -> four code words + 64 other bits
+__attribute__((target("avx512f,avx512bw,bmi2"))) inline void pack64_avx512(const uint8_t* s, uint64_t& c_lo, uint64_t& c_hi, uint64_t& other) {
+  const __m512i v = _mm512_loadu_si512(reinterpret_cast<const void*>(s));
+  const __mmask64 valid = _mm512_cmpeq_epi8_mask(v, _mm512_set1_epi8('A')) | _mm512_cmpeq_epi8_mask(v, _mm512_set1_epi8('C')) |
+                          _mm512_cmpeq_epi8_mask(v, _mm512_set1_epi8('G')) | _mm512_cmpeq_epi8_mask(v, _mm512_set1_epi8('T'));
+  const __mmask64 p0 = _mm512_test_epi8_mask(v, _mm512_set1_epi8(0x02)), p1 = _mm512_test_epi8_mask(v, _mm512_set1_epi8(0x04));
+  const uint64_t b1 = (uint64_t)p1 & (uint64_t)valid, b0 = ((uint64_t)p0 ^ (uint64_t)p1) & (uint64_t)valid;
+  c_lo = _pdep_u64(b0 & 0xFFFFFFFFull, 0x5555555555555555ull) | _pdep_u64(b1 & 0xFFFFFFFFull, 0xAAAAAAAAAAAAAAAAull);
+  c_hi = _pdep_u64(b0 >> 32, 0x5555555555555555ull) | _pdep_u64(b1 >> 32, 0xAAAAAAAAAAAAAAAAull);
+  other = ~(uint64_t)valid;
 }
 #endif
 
-void pack_range_scalar(const uint8_t* src, uint64_t w0, uint64_t w1, uint64_t nbytes, uint32_t* codes, uint16_t* other) {
-  for (uint64_t w = w0; w < w1; ++w) {
-    const uint64_t at = w * 16;
-    const uint32_t n = at >= nbytes ? 0u : (uint32_t)(nbytes - at < 16 ? nbytes - at : 16);
-    pack16_scalar(src + at, n, codes[w], other[w]);
+// One 512-base block (32 source words from byte offset `at`): codes out, the block's `other` masks into oth[32].
+// Returns the OR of the masks.  `nbytes` bounds the reads (bytes past it pack as code 0, other 0).
+template <int LEVEL>
+#if defined(__x86_64__)
+__attribute__((target("avx512f,avx512bw,avx2,bmi2")))
+#endif
+inline uint32_t pack_block(const uint8_t* src, uint64_t at, uint64_t nbytes, uint32_t* codes, uint16_t* oth) {
+  uint32_t any = 0;
+  if (at + 512 <= nbytes) {
+#if defined(__x86_64__)
+    if (LEVEL == 2) {
+      for (int k = 0; k < 8; ++k) {
+        uint64_t lo, hi, o;
+        pack64_avx512(src + at + 64 * k, lo, hi, o);
+        codes[4 * k] = (uint32_t)lo; codes[4 * k + 1] = (uint32_t)(lo >> 32);
+        codes[4 * k + 2] = (uint32_t)hi; codes[4 * k + 3] = (uint32_t)(hi >> 32);
+        oth[4 * k] = (uint16_t)o; oth[4 * k + 1] = (uint16_t)(o >> 16); oth[4 * k + 2] = (uint16_t)(o >> 32); oth[4 * k + 3] = (uint16_t)(o >> 48);
+        any |= (o != 0);
+      }
+      return any;
+    }
+    if (LEVEL == 1) {
+      for (int k = 0; k < 16; ++k) {
+        uint64_t c;
+        uint32_t o;
+        pack32_avx2(src + at + 32 * k, c, o);
+        codes[2 * k] = (uint32_t)c; codes[2 * k + 1] = (uint32_t)(c >> 32);
+        oth[2 * k] = (uint16_t)o; oth[2 * k + 1] = (uint16_t)(o >> 16);
+        any |= o;
+      }
+      return any;
+    }
+#endif
   }
+  for (int w = 0; w < 32; ++w) {
+    const uint64_t a = at + 16 * (uint64_t)w;
+    const uint32_t n = a >= nbytes ? 0u : (uint32_t)(nbytes - a < 16 ? nbytes - a : 16);
+    pack16_scalar(src + a, n, codes[w], oth[w]);
+    any |= oth[w];
+  }
+  return any;
 }
 
 }  // namespace
 
-uint64_t nq_pack_words(uint64_t nbytes) { return (kPackLead + nbytes + 15) / 16 + kPackTailWords; }
-uint64_t nq_pack_blocks(uint64_t nbytes) { return (nq_pack_words(nbytes) + 31) / 32; }
+uint64_t nq_pack_words(uint64_t nbytes) { return ((kPackLead + nbytes + 15) / 16 + kPackTailWords + 31) / 32 * 32; }  // whole blocks
+uint64_t nq_pack_blocks(uint64_t nbytes) { return nq_pack_words(nbytes) / 32; }
 
-// codes[words], blk[blocks], pool[(pool_cap) * 32], dense[words] = caller-provided scratch (u16 per word).
-// Returns the number of pool slots used, or ~0ull when pool_cap is too small.
+// codes[words], blk[blocks], pool[pool_cap * 32].  Returns the pool slots used, or ~0ull when pool_cap is
+// too small.  Blocks are packed by `threads` workers (tasks of 1 MiB of sequence); a block with a byte
+// that is not upper-case ACGT leaves its 32 mask words in the task's own list, and the lists are laid
+// into the pool in task order afterwards, so the result does not depend on the thread count.
 uint64_t nq_pack_host(const char* bases, uint64_t nbytes, const uint64_t* rec_offsets, uint64_t n_rec, uint32_t K,
-                      uint32_t* codes, uint32_t* blk, uint16_t* pool, uint64_t pool_cap, uint16_t* dense, unsigned threads) {
+                      uint32_t* codes, uint32_t* blk, uint16_t* pool, uint64_t pool_cap, unsigned threads) {
   const uint8_t* src = reinterpret_cast<const uint8_t*>(bases);
-  const uint64_t words = nq_pack_words(nbytes), blocks = nq_pack_blocks(nbytes);
-  constexpr uint64_t lead_w = kPackLead / 16;  // a whole block: source word w lands at packed word w + lead_w
-  for (uint64_t w = 0; w < lead_w; ++w) { codes[w] = 0; dense[w] = 0; }
-  blk[0] = 0xFFFFFFFFu;
-  const uint64_t src_words = words - lead_w;
+  const uint64_t blocks = nq_pack_blocks(nbytes);
+  constexpr uint64_t lead_b = kPackLead / 512;  // source block b lands at packed block b + lead_b
+  for (uint64_t w = 0; w < lead_b * 32; ++w) codes[w] = 0;
+  for (uint64_t b = 0; b < lead_b; ++b) blk[b] = 0xFFFFFFFFu;
+  const uint64_t src_blocks = blocks - lead_b;
   if (threads == 0) threads = 1;
-  const uint64_t chunk = 1 << 16;  // source words per task (1 MiB of sequence, 2048 blocks)
-  const uint64_t tasks = (src_words + chunk - 1) / chunk;
+  const uint64_t chunk = 2048;  // source blocks per task (1 MiB of sequence)
+  const uint64_t tasks = (src_blocks + chunk - 1) / chunk;
+  struct TaskOut { std::vector<uint16_t> masks; std::vector<uint64_t> which; };
+  std::vector<TaskOut> outs(tasks);
   std::atomic<uint64_t> next{0};
+  const int level = simd_level();
   auto work = [&]() {
     for (;;) {
       const uint64_t t = next.fetch_add(1);
       if (t >= tasks) break;
-      const uint64_t w0 = t * chunk, w1 = w0 + chunk < src_words ? w0 + chunk : src_words;
-#if defined(__x86_64__)
-      if (have_avx2()) pack_range_avx2(src, w0, w1, nbytes, codes + lead_w, dense + lead_w);
-      else
-#endif
-        pack_range_scalar(src, w0, w1, nbytes, codes + lead_w, dense + lead_w);
-      // which 512-base blocks hold a byte that is not upper-case ACGT
-      for (uint64_t b0 = w0; b0 < w1; b0 += 32) {
-        const uint64_t e = b0 + 32 < w1 ? b0 + 32 : w1;
-        uint16_t any = 0;
-        for (uint64_t w = b0; w < e; ++w) any |= dense[lead_w + w];
-        blk[(lead_w + b0) / 32] = any ? 1u : 0xFFFFFFFFu;
+      const uint64_t b0 = t * chunk, b1 = b0 + chunk < src_blocks ? b0 + chunk : src_blocks;
+      TaskOut& out = outs[t];
+      uint16_t oth[32];
+      for (uint64_t b = b0; b < b1; ++b) {
+        uint32_t* c = codes + (lead_b + b) * 32;
+        const uint32_t any = level == 2 ? pack_block<2>(src, b * 512, nbytes, c, oth)
+                             : level == 1 ? pack_block<1>(src, b * 512, nbytes, c, oth) : pack_block<0>(src, b * 512, nbytes, c, oth);
+        if (any) {
+          out.which.push_back(lead_b + b);
+          out.masks.insert(out.masks.end(), oth, oth + 32);
+        } else {
+          blk[lead_b + b] = 0xFFFFFFFFu;
+        }
       }
     }
   };
   const unsigned nt = (unsigned)(tasks < threads ? (tasks ? tasks : 1) : threads);
-  if (nt <= 1) {
-    work();
-  } else {
-    std::vector<std::thread> pool_threads;
-    pool_threads.reserve(nt - 1);
-    for (unsigned i = 1; i < nt; ++i) pool_threads.emplace_back(work);
-    work();
-    for (auto& th : pool_threads) th.join();
+  if (nt <= 1) work();
+  else Workers::get().run(nt - 1, work);
+  // sparse `other` masks: the flagged blocks, in stream order
+  uint64_t used = 0;
+  for (uint64_t t = 0; t < tasks; ++t) {
+    const TaskOut& out = outs[t];
+    if (used + out.which.size() > pool_cap) return ~0ull;
+    for (size_t i = 0; i < out.which.size(); ++i) {
+      memcpy(pool + (used + i) * 32, out.masks.data() + i * 32, 64);
+      blk[out.which[i]] = (uint32_t)(used + i);
+    }
+    used += out.which.size();
   }
   // seeds: the first K-1 characters of every record (:255-273, :340-341)
   for (uint64_t r = 0; r < n_rec; ++r) {
@@ -172,19 +272,9 @@ uint64_t nq_pack_host(const char* bases, uint64_t nbytes, const uint64_t* rec_of
       const uint64_t p = kPackLead + e0 + j;
       const uint32_t code = ok ? seed_code_of(src[e0 + j]) : 0u, sh = 2 * (uint32_t)(p & 15);
       codes[p >> 4] = (codes[p >> 4] & ~(3u << sh)) | (code << sh);
-      dense[p >> 4] &= (uint16_t)~(1u << (p & 15));
+      const uint32_t slot = blk[p >> 9];
+      if (slot != 0xFFFFFFFFu) pool[(uint64_t)slot * 32 + ((p >> 4) & 31)] &= (uint16_t)~(1u << (p & 15));
     }
-  }
-  // sparse `other` masks: flagged blocks get a pool slot (a block whose only such bytes sat in a seed
-  // keeps a slot of zeros)
-  uint64_t used = 0;
-  for (uint64_t b = 0; b < blocks; ++b) {
-    if (blk[b] == 0xFFFFFFFFu) continue;
-    if (used >= pool_cap) return ~0ull;
-    const uint64_t w0 = b * 32, w1 = w0 + 32 < words ? w0 + 32 : words;
-    uint16_t* slot = pool + used * 32;
-    for (uint64_t w = w0; w < w0 + 32; ++w) slot[w - w0] = w < w1 ? dense[w] : 0;
-    blk[b] = (uint32_t)used++;
   }
   return used;
 }

@@ -451,10 +451,15 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
   if (n_entries == 0) return NQ_OK;
   if (n >= (1ull << 31) || n_entries >= (1ull << 31))
     return nq_set_error(NQ_ERR_INVALID, "too many entries in one batch: %llu", (unsigned long long)n);
-  if (h_rec_entry)
-    for (uint64_t e = 0; e < n; ++e)
+  if (h_rec_entry) {
+    bool identity = n == n_entries;
+    for (uint64_t e = 0; e < n; ++e) {
       if (h_rec_entry[e] >= n_entries) return nq_set_error(NQ_ERR_INVALID, "record %llu maps to entry %u >= %llu",
                                                            (unsigned long long)e, h_rec_entry[e], (unsigned long long)n_entries);
+      identity = identity && h_rec_entry[e] == e;
+    }
+    if (identity) h_rec_entry = nullptr;  // one record per entry (lines mode): the fused short-entry kernel applies
+  }
   if ((reinterpret_cast<uintptr_t>(d_bases) & 15) != 0)
     return nq_set_error(NQ_ERR_INVALID, "d_bases must be 16-byte aligned");
   if (bases_capacity < h_offsets[n])
@@ -480,8 +485,9 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
     if (!(env && env[0] == '0')) {
       static const char* dens_env = nq_tuning_env("NQ_READS_DENSIFY");  // "cell": the all-cells densification (measurement only)
       const bool listed = !(dens_env && dens_env[0] == 'c');
-      uint64_t* d_offsets = nullptr;
-      NQ_TRY(nq_dmalloc(ctx, (void**)&d_offsets, (n + 1) * sizeof(uint64_t)));
+      NqScratch s_off(ctx);
+      NQ_TRY(nq_dmalloc(ctx, &s_off.p, (n + 1) * sizeof(uint64_t)));
+      uint64_t* d_offsets = s_off.as<uint64_t>();
       NQ_CUDA(cudaMemcpyAsync(d_offsets, h_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
       auto launch = [&](auto kern, int nw, size_t smem) -> int {
         NQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -497,10 +503,9 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
       if (!listed) lst = launch(sketch_reads_kernel<8, false>, 8, (size_t)8 * 2 * P.F * 4);
       else if (P.F <= 1024) lst = launch(sketch_reads_kernel<8, true>, 8, (size_t)8 * 4 * P.F * 4);
       else lst = launch(sketch_reads_kernel<4, true>, 4, (size_t)4 * 4 * P.F * 4);
-      if (lst != NQ_OK) { nq_dfree(ctx, d_offsets); return lst; }
+      if (lst != NQ_OK) return lst;
       ctx->launches++;
       const cudaError_t le = cudaPeekAtLastError();
-      nq_dfree(ctx, d_offsets);
       if (le != cudaSuccess) return nq_set_error(NQ_ERR_CUDA, "sketch_reads_kernel launch failed: %s", cudaGetErrorString(le));
       return NQ_OK;
     }
@@ -510,11 +515,11 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
   span_len = std::max<uint64_t>(span_len, 65536);
   const bool sliced = longest > span_len || h_rec_entry != nullptr;  // a record->row map needs spans
 
-  uint64_t* d_offsets = nullptr;
-  Span* d_spans = nullptr;
+  NqScratch s_offsets(ctx), s_spans(ctx);  // returned on every path out
   uint64_t nblocks = n;
-  NQ_TRY(nq_dmalloc(ctx, (void**)&d_offsets, (n + 1) * sizeof(uint64_t)));
-  NQ_CUDA(cudaMemcpyAsync(d_offsets, h_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  NQ_TRY(nq_dmalloc(ctx, &s_offsets.p, (n + 1) * sizeof(uint64_t)));
+  uint64_t* d_offsets = s_offsets.as<uint64_t>();
+  NQ_TRY(nq_upload_small(ctx, d_offsets, h_offsets, (n + 1) * sizeof(uint64_t)));
   std::vector<Span> spans;
   if (sliced) {
     for (uint64_t e = 0; e < n; ++e) {
@@ -527,10 +532,10 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
         spans.push_back(Span{e0 + a, e0 + std::min(nk, a + each), e0, h_rec_entry ? h_rec_entry[e] : (uint32_t)e, 0});
     }
     nblocks = spans.size();
-    NQ_TRY(nq_dmalloc(ctx, (void**)&d_spans, spans.size() * sizeof(Span)));
-    NQ_CUDA(cudaMemcpyAsync(d_spans, spans.data(), spans.size() * sizeof(Span), cudaMemcpyHostToDevice, ctx->stream));
-    NQ_CUDA(cudaStreamSynchronize(ctx->stream));  // `spans` is pageable host memory
+    NQ_TRY(nq_dmalloc(ctx, &s_spans.p, spans.size() * sizeof(Span)));
+    NQ_TRY(nq_upload_small(ctx, s_spans.p, spans.data(), spans.size() * sizeof(Span)));  // through the pinned ring: no host stall
   }
+  const Span* d_spans = s_spans.as<Span>();
 
   const uint8_t* b = reinterpret_cast<const uint8_t*>(d_bases);
   uint32_t* sk = reinterpret_cast<uint32_t*>(d_sketches);
@@ -552,8 +557,6 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
     st = small ? launch_scan<false, 128>(ctx, PG, b, d_offsets, d_spans, nblocks, sk)
                : launch_scan<false, 1024>(ctx, PG, b, d_offsets, d_spans, nblocks, sk);
   }
-  nq_dfree(ctx, d_offsets);
-  nq_dfree(ctx, d_spans);
   NQ_TRY(st);
   return nq_launch_densify(ctx, p, d_sketches, n_entries, d_flags);
 }

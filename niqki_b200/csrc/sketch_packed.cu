@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_packed_kernel(PackedIn in, 
       const uint32_t ylo = __funnelshift_r(c0, c1, s), yhi = __funnelshift_r(c1, c2, s);
       uint32_t fhi, flo;
       if (fsh < 32) { fhi = xhi >> fsh; flo = __funnelshift_r(xlo, xhi, fsh); }
-      else { fhi = 0; flo = fsh == 32 ? xhi : xhi >> (fsh - 32); }
+      else { fhi = 0; flo = xhi >> ((fsh - 32) & 31); }
       emit(fhi, flo, yhi & kmask_hi, ylo & kmask_lo);
     };
     const uint64_t mf = (lo + 15) >> 4, ml = hi >> 4;  // full words [mf, ml)
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_packed_kernel(PackedIn in, 
           } else {
             const uint32_t xhi = j ? __funnelshift_l(b1, b0, 2 * j) : b0, xlo = j ? __funnelshift_l(b2, b1, 2 * j) : b1;
             if (fsh < 32) { fhi = xhi >> fsh; flo = __funnelshift_r(xlo, xhi, fsh); }
-            else { fhi = 0; flo = fsh == 32 ? xhi : xhi >> (fsh - 32); }
+            else { fhi = 0; flo = xhi >> ((fsh - 32) & 31); }
             rlo = (j ? __funnelshift_r(c0, c1, 2 * j) : c0) & kmask_lo;
             rhi = (j ? __funnelshift_r(c1, c2, 2 * j) : c1) & kmask_hi;
           }
@@ -240,11 +240,12 @@ int nq_launch_sketch_packed(nq_ctx* ctx, const nq_params* p, const uint32_t* d_c
   }
   Span* d_spans = nullptr;
   NQ_TRY(nq_dmalloc(ctx, (void**)&d_spans, spans.size() * sizeof(Span)));
-  cudaError_t ce = cudaMemcpyAsync(d_spans, spans.data(), spans.size() * sizeof(Span), cudaMemcpyHostToDevice, ctx->stream);
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);  // `spans` is pageable host memory
-  if (ce != cudaSuccess) {
-    nq_dfree(ctx, d_spans);
-    return nq_set_error(NQ_ERR_CUDA, "span upload failed: %s", cudaGetErrorString(ce));
+  {
+    const int us = nq_upload_small(ctx, d_spans, spans.data(), spans.size() * sizeof(Span));  // pinned ring: no host stall
+    if (us != NQ_OK) {
+      nq_dfree(ctx, d_spans);
+      return us;
+    }
   }
   const PackedIn in{d_codes, d_blk, d_pool};
   uint32_t* sk = reinterpret_cast<uint32_t*>(d_sketches);

@@ -8,6 +8,7 @@ buffers; objects exposing ``data_ptr()`` (torch CUDA tensors) are passed as devi
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -39,9 +40,15 @@ class Context:
         check(self.L.nq_ctx_create(device, sp, C.byref(h)))
         self.h = h
         self.device = device
+        # a context that owns its stream is not ordered against the caller's (torch's) stream: the
+        # device-pointer methods of Index then fence on both sides (see Index._fence_in / _fence_out)
+        self.own_stream = stream is None
+        self._indexes = weakref.WeakSet()  # posting lists living on this context: freed before it (nq_index_free uses the ctx)
 
     def close(self):
         if getattr(self, "h", None):
+            for ix in list(getattr(self, "_indexes", ())):
+                ix.close_index()
             self.L.nq_ctx_destroy(self.h)
             self.h = None
 
@@ -76,6 +83,11 @@ class Context:
         return out
 
     @property
+    def h2d_bytes(self) -> int:
+        """Bytes of sequence (packed or not) the host-buffer sketch calls have copied to the device so far."""
+        return int(self.L.nq_ctx_h2d_bytes(self.h))
+
+    @property
     def last_query_gathered(self) -> int:
         return int(self.L.nq_ctx_last_query_gathered(self.h))
 
@@ -96,6 +108,7 @@ class Index:
             self.select_best_H(genome_size)
         self._own_ctx = ctx is None
         self.ctx = ctx if ctx is not None else Context(device)
+        self.ctx._indexes.add(self)
         self.ix = None
         self.gid_base = 0
         self.genome_numbers = 0
@@ -122,6 +135,20 @@ class Index:
 
     __del__ = close
 
+    # ---- stream ordering of the device-pointer forms: the library launches on the context's stream and
+    # returns without syncing.  When that stream is torch's current stream (Context(device, stream)) the
+    # calls are ordered like any other torch op.  When the context owns a stream of its own, inputs
+    # produced on torch's stream must be complete before the call and outputs before torch reads them.
+    def _fence_in(self, t):
+        if self.ctx.own_stream and _is_device(t):
+            import torch
+
+            torch.cuda.current_stream(t.device).synchronize()
+
+    def _fence_out(self):
+        if self.ctx.own_stream:
+            self.ctx.sync()
+
     # ---- sketching (compute_sketch + sketch_densification)
     def compute_sketches(self, bases, offsets, out=None, flags=None):
         """Batch form of Index::compute_sketch on fresh sketches.  ``bases`` u8 (numpy = host,
@@ -135,8 +162,10 @@ class Index:
                 out = torch.empty((n, self.F), dtype=torch.int32, device=bases.device)
             if flags is None:
                 flags = torch.empty((max(n, 1),), dtype=torch.int32, device=bases.device)
+            self._fence_in(bases)
             check(self.L.nq_sketch_batch_device(self.ctx.h, C.byref(self.p), _ptr(bases), bases.numel(), _ptr(offsets),
                                                 n, _ptr(out), _ptr(flags)))
+            self._fence_out()
             return out, flags[:n]
         bases = np.ascontiguousarray(bases, np.uint8)
         if out is None:
@@ -189,7 +218,9 @@ class Index:
         import torch
 
         flags = torch.zeros((sketches.shape[0],), dtype=torch.int32, device=sketches.device)
+        self._fence_in(sketches)
         check(self.L.nq_densify_device(self.ctx.h, C.byref(self.p), _ptr(sketches), sketches.shape[0], _ptr(flags)))
+        self._fence_out()
         return sketches, flags
 
     # ---- index (insert_sketch over a batch)
@@ -201,6 +232,7 @@ class Index:
         n = int(sketches.shape[0])
         h = C.c_void_p()
         if _is_device(sketches):
+            self._fence_in(sketches)
             check(self.L.nq_index_build_device(self.ctx.h, C.byref(self.p), _ptr(sketches), n, gid_base, C.byref(h)))
         else:
             sk = np.ascontiguousarray(sketches, np.int32)
@@ -240,6 +272,7 @@ class Index:
         nq = int(sketches.shape[0])
         h = C.c_void_p()
         if _is_device(sketches):
+            self._fence_in(sketches)
             check(self.L.nq_query_batch_device(self.ix, _ptr(sketches), nq, ms, C.byref(h) if fetch else None))
             if not fetch:
                 return None

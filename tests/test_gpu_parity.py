@@ -656,7 +656,7 @@ def test_packed_path_random_and_long_vs_oracle(nb, packed_ctx):
             s = rng.choice(np.frombuffer(alpha, np.uint8), size=int(rng.integers(ps["K"] + 1, 3000)), p=pr)
             if o.compute_sketch(s, max_passes=100000)[1] >= 0:
                 seqs.append(s)
-        seqs += [b"ACGT" * 3, b"", b"A" * ps["K"]]
+        seqs += [b"ACGT" * 2, b"", b"A" * ps["K"]]  # len <= K (all K here are >= 11): skipped entries
         sks, flags = g.sketch_many(seqs)
         assert np.array_equal(sks, o.sketch_many(seqs)), ps
         assert list(flags[-3:]) == [1, 1, 1] and not flags[:-3].any()
@@ -690,3 +690,54 @@ def test_packed_and_character_paths_agree_on_a_multi_batch_call(nb, ctx, packed_
     assert np.array_equal(a, b)
     o = oracle(K=31, S=10, W=12, H=4)
     assert np.array_equal(a[:2], o.sketch_many(seqs[:2]))
+
+
+@pytest.mark.parametrize("W,H,n", [(13, 4, 3000), (15, 5, 3000), (14, 4, 70_000), (15, 4, 200)])
+def test_index_and_query_with_wide_fingerprints(nb, ctx, W, H, n):
+    """W = 13..15: 2^W counters of a cell no longer fit eight warps' worth of shared memory; the build
+    kernels size themselves.  Postings and hits against the oracle."""
+    rng = np.random.default_rng(W * 1000 + n)
+    ps = dict(K=31, S=6, W=W, H=H)
+    F = 64
+    o = oracle(J=0.1, **ps)
+    g = gpu_index(nb, ctx, J=0.1, **ps)
+    sks = rng.integers(0, 1 << W, size=(n, F)).astype(np.int32)
+    dup = rng.random((n, F)) < 0.3
+    sks[dup] = np.broadcast_to(sks[0], (n, F))[dup]     # shared fingerprints: lists of ~0.3 n
+    sks[rng.random((n, F)) < 0.01] = -1
+    g.insert_sketches(sks)
+    o.insert_sketches(sks)
+    rp, ogids = o.csr()
+    sizes, gids = g.export_postings()
+    assert np.array_equal(sizes, np.diff(rp).astype(np.uint32))
+    assert np.array_equal(gids, ogids)
+    q = np.concatenate([sks[:4], rng.integers(0, 1 << W, size=(4, F)).astype(np.int32)])
+    ptr, c, gid = g.query_sketches(q)
+    ohp, oc, og = o.query_batch(q)
+    assert np.array_equal(ptr, ohp) and np.array_equal(c, oc) and np.array_equal(gid, og)
+
+
+def test_import_of_unsorted_lists(nb, ctx):
+    """The reference's own dumps hold a list in the order its OpenMP threads appended.
+    Import must not depend on it: shuffled lists, more than 65600 genomes (split16 directory)."""
+    rng = np.random.default_rng(99)
+    n, F = 66_000, 32
+    ps = dict(K=31, S=5, W=12, H=4)
+    o = oracle(J=0.2, **ps)
+    g = gpu_index(nb, ctx, J=0.2, **ps)
+    sks = (rng.integers(0, 4096, size=(n, F)) & rng.integers(0, 4096, size=(n, F))).astype(np.int32)
+    sks[rng.random(n) < 0.2] = sks[1]
+    o.insert_sketches(sks)
+    rp, ogids = o.csr()
+    sizes = np.diff(rp).astype(np.uint32)
+    shuffled = ogids.copy()
+    for l in np.flatnonzero(sizes > 1)[:200000]:
+        seg = shuffled[int(rp[l]):int(rp[l + 1])]
+        rng.shuffle(seg)
+    g.import_postings(sizes, shuffled, n)
+    q = np.concatenate([sks[:3], sks[n - 3:]])
+    ptr, c, gid = g.query_sketches(q)
+    ohp, oc, og = o.query_batch(q)
+    assert np.array_equal(ptr, ohp) and np.array_equal(c, oc) and np.array_equal(gid, og)
+    s2, g2 = g.export_postings()
+    assert np.array_equal(s2, sizes) and np.array_equal(g2, ogids)   # lists come back gid-ascending

@@ -46,6 +46,43 @@ __global__ void k_smem_min_filtered(uint32_t words, int iters, uint32_t* sink) {
   if (threadIdx.x == 0) sink[blockIdx.x] = sm[0];
 }
 
+// INT32 issue rate of an SM (the roofline denominator of the sketch scan): chains of independent integer
+// instructions, 8 per thread, timed with clock64() on the device so that the result is ops per clock
+// and does not depend on the clock the box happens to run at.  MIX 0: LOP3 + IADD3 (ALU pipe),
+// 1: IMAD (FMA pipe), 2: 3 IMAD : 4 ALU, close to the mix of the scan kernel's inner loop (15 : 19).
+template <int MIX>
+__global__ void __launch_bounds__(1024) k_int_rate(int iters, uint32_t seed, uint32_t* sink, unsigned long long* cycles) {
+  uint32_t x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = seed + threadIdx.x * 8 + i;
+  const uint32_t c = seed | 1u, d = seed * 3u + 7u;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (MIX == 0) {           // 2 ops
+        x[i] = (x[i] ^ d) + c;
+      } else if (MIX == 1) {    // 1 op
+        x[i] = x[i] * c + d;
+      } else {                  // 7 instructions: 3 IMAD, SHF, 2 LOP3, IADD3 (checked in the SASS)
+        x[i] = x[i] * c + d;
+        x[i] ^= x[i] >> 3;
+        x[i] = x[i] * d + c;
+        x[i] = (x[i] & d) | c;
+        x[i] = x[i] * c + x[(i + 1) & 7];
+        x[i] = x[i] + __brev(d);
+      }
+    }
+  }
+  const long long t1 = clock64();
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc ^= x[i];
+  if (acc == 0x12345678u) sink[0] = acc;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+}
+
 template <typename F>
 static float timeit(F f) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -82,6 +119,26 @@ int main() {
     float ms = timeit([&] { k_red_global<<<sms * 8, 256>>>(tab, words, 1024); });
     printf("global RED.ADD random    table=%4u MB      : %8.1f Gops/s\n", words >> 18, (double)sms * 8 * 256 * 1024 / ms / 1e6);
     cudaFree(tab);
+  }
+  {
+    unsigned long long* cyc; cudaMalloc(&cyc, sms * 2 * sizeof(unsigned long long));
+    unsigned long long h[2048];
+    const int it = 2048;
+    auto rate = [&](auto kern, int ops_per_elem, const char* what) {
+      kern<<<sms * 2, 1024>>>(it, 12345u, sink, cyc); cudaDeviceSynchronize();
+      kern<<<sms * 2, 1024>>>(it, 12345u, sink, cyc); cudaDeviceSynchronize();
+      cudaMemcpy(h, cyc, sms * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      double mean = 0; for (int i = 0; i < sms * 2; ++i) mean += (double)h[i]; mean /= sms * 2;
+      // two 1024-thread CTAs share an SM for (about) the same `mean` cycles
+      const double per_clk = 2.0 * 1024 * 8.0 * ops_per_elem * it / mean;
+      printf("int32 %-28s : %6.1f ops/clk/SM\n", what, per_clk);
+      return per_clk;
+    };
+    rate(k_int_rate<0>, 2, "LOP3+IADD3 (ALU pipe)");
+    rate(k_int_rate<1>, 1, "IMAD (FMA pipe)");
+    const double mix = rate(k_int_rate<2>, 7, "3 IMAD : 4 ALU (scan mix)");
+    printf("{\"int32_ops_per_clk_per_sm\": %.2f, \"source\": \"tools/microbench k_int_rate<2>: 3 IMAD : 4 ALU instructions, 2 x 1024 threads per SM, clock64\"}\n", mix);
+    cudaFree(cyc);
   }
   float ms = timeit([&] { k_match<<<sms * 8, 256>>>(1024, sink); });
   printf("__match_any_sync                              : %8.1f G lane-ops/s\n", (double)sms * 8 * 256 * 1024 / ms / 1e6);
