@@ -518,11 +518,12 @@ def run_c4(args):
 
 
 def run_c5(args):
-    """Secondary line, configs[4]: all-vs-all --matrix of N genomes at S=18.  Every rank sketches its
-    slice of the genomes, the sketches are all-gathered, every rank builds the whole index and
-    computes its block of rows.  Timed: the matrix rows (device counting + D2H of the
-    dense counts); sketching and index build are reported beside it."""
+    """Secondary line, configs[4]: all-vs-all --matrix of N genomes at S=18, the genome x genome grid tiled
+    over the GPUs: the index is sharded by genome id like everywhere else; the rows of one
+    shard at a time are broadcast (nq_bcast_sketches, NCCL, u16 on the wire) and every GPU counts them
+    against its own columns (nq_matrix_tile), dense counts to the host.  Timed: the whole matrix."""
     from niqki_b200.capi import check, lib
+    from niqki_b200.shard import Comm, torch_bcast_bytes
 
     torch, dist, niqki_b200, world, rank, local, dev, stream, ctx, barrier, timed = _setup(args)
     S5 = 18
@@ -530,13 +531,13 @@ def run_c5(args):
     L = args.genome_len
     Lc = lib()
     ix = niqki_b200.Index(S=S5, K=K, W=W, H=H, min_fract=J, ctx=ctx)
+    comm = Comm(ctx, rank, world, torch_bcast_bytes(dist, dev)) if world > 1 else None
     F = ix.F
     per = (N + world - 1) // world
-    g0, g1 = rank * per, min(N, (rank + 1) * per)
+    g0, g1 = min(N, rank * per), min(N, (rank + 1) * per)
     B = 2000
     buf = torch.empty(B * L + 64, dtype=torch.uint8, device=dev)
-    sk = torch.empty((per * world, F), dtype=torch.int32, device=dev)
-    mine = sk[g0:g0 + per]
+    mine = torch.empty((max(g1 - g0, 1), F), dtype=torch.int32, device=dev)
     ctx.set_timing(True)
     ctx.timing_reset()
     torch.cuda.synchronize()
@@ -544,25 +545,39 @@ def run_c5(args):
     for b0 in range(g0, g1, B):
         nb = min(B, g1 - b0)
         check(Lc.nq_synth_genomes_device(ctx.h, SEED, b0, nb, L, C.c_void_p(buf.data_ptr())))
-        ix.compute_sketches(buf, np.arange(nb + 1, dtype=np.uint64) * L, out=sk[b0:b0 + nb])
+        ix.compute_sketches(buf, np.arange(nb + 1, dtype=np.uint64) * L, out=mine[b0 - g0:b0 - g0 + nb])
     torch.cuda.synchronize()
     t_sk = time.perf_counter() - t_sk
     scan_ms, scan_n = ctx.timing()["scan"]
     del buf
-    if world > 1:
-        dist.all_gather_into_tensor(sk, mine.clone())
     t_ix = time.perf_counter()
-    ix.insert_sketches(sk[:N], gid_base=0)
+    ix.insert_sketches(mine[: g1 - g0], gid_base=g0)
     torch.cuda.synchronize()
     t_ix = time.perf_counter() - t_ix
-    del sk, mine
-    rows = g1 - g0
+    RB = 1000   # rows per broadcast block
+    d_rows = torch.empty((RB, F), dtype=torch.int32, device=dev)
     out = {}
 
-    def step():
-        out["m"] = ix.query_range(g0, g1, wrap16=True)
+    def step(check_tiles=False):
+        diag = True
+        incr = 0.0
+        for owner in range(world):
+            o0, o1 = min(N, owner * per), min(N, (owner + 1) * per)
+            for b0 in range(o0, o1, RB):
+                nb = min(RB, o1 - b0)
+                if rank == owner:
+                    d_rows[:nb].copy_(mine[b0 - g0:b0 - g0 + nb])
+                if world > 1:
+                    comm.bcast_sketches(ix.p, d_rows[:nb], owner)
+                tile = ix.matrix_tile(d_rows[:nb], wrap16=True)    # [nb][g1 - g0] on the host
+                if check_tiles:  # untimed pass only: checksum of the tiles and the diagonal (a genome against itself: F mod 2^16)
+                    incr += float(tile.sum(dtype=np.float64))
+                    if rank == owner:
+                        diag = diag and bool(np.all(tile[np.arange(nb), np.arange(b0 - g0, b0 - g0 + nb)] == (F & 0xFFFF)))
+        if check_tiles:
+            out["diag"], out["incr"] = diag, incr
 
-    step()
+    step(check_tiles=True)
     ctx.timing_reset()
     launches0 = ctx.launches
     sampler = ClockSampler(local)
@@ -574,28 +589,40 @@ def run_c5(args):
         step()
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    agg = torch.tensor([out["incr"], 1.0 if out["diag"] else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
     clocks = sampler.stop() if rank == 0 else None
     m_ms, m_n = ctx.timing()["matrix"]
     launches = ctx.launches - launches0
-    m = out["m"]
-    diag_ok = bool(np.all(m[np.arange(rows), np.arange(g0, g1)] == (F & 0xFFFF)))
     if rank == 0:
         sec = float(dt.item()) / args.steps
-        pair_incr = float(m.astype(np.float64).sum()) * world  # ~ total increments (this rank's rows x ranks)
+        peaks = _peaks()
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        info = ix.info()
+        # K4b algorithmic bytes of this rank's tiles: the postings its probes gather (4 B each,
+        # ~ the pair increments of wrapped counters are a lower bound; the true figure is the gathered ids),
+        # row pairs + u16 sketch per probed cell, dense counts out
+        m_bytes = 4.0 * float(agg[0].item()) / world + N * F * (8 + 2) + 4.0 * N * (g1 - g0)
+        m_gbs = m_bytes / (m_ms / args.steps / 1e3) / 1e9 if m_ms else None
         line = {"metric": "genome pairs/s (all-vs-all --matrix, S=18)", "value": N * N / sec, "unit": "pairs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": {"workload": f"secondary (not the contract line) configs[4]: --matrix of {N} synthetic {L} bp genomes, S={S5}, "
-                                       f"rows tiled over {world} GPU(s)", "K": K, "S": S5, "W": W, "H": H,
-                           "l2": "index (directory + postings) far larger than L2"},
+                                       f"genome x genome grid tiled over {world} GPU(s): index sharded by genome id, row blocks of {RB} "
+                                       f"broadcast (nq_bcast_sketches), every GPU counts them against its own columns (nq_matrix_tile)",
+                           "K": K, "S": S5, "W": W, "H": H, "l2": "index (directory + postings) far larger than L2"},
                 "matrix_device_ms_per_step": m_ms / args.steps, "matrix_kernel_launches": int(m_n),
-                "pair_increments_per_s": pair_incr / (m_ms / args.steps / 1e3) if m_ms else None,
+                "pair_increments_per_s": float(agg[0].item()) / sec,
                 "sketch_gbases_per_s": (g1 - g0) * L / (scan_ms / 1e3) / 1e9 if scan_ms else None, "sketch_wall_s": t_sk,
-                "index_build_wall_s": t_ix, "diag_is_F_mod_65536": diag_ok,
-                "e2e": {"value": N * N / sec, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(m.nbytes),
-                        "note": "nq_matrix_rows: dense u32 counts of this rank's rows copied to the host"},
+                "index_build_wall_s": t_ix, "index_bytes_per_gpu": info["device_bytes"],
+                "diag_is_F_mod_65536": bool(agg[1].item() == world),
+                "roofline": {"kernel": "matrix tiles = the query kernels with a dense epilogue", "bound": "hbm", "achieved": m_gbs, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": (m_gbs / hbm_peak) if m_gbs else None, "traffic": None, "algorithmic_bytes": m_bytes,
+                             "note": "rank 0's tiles; gathered postings counted as the wrapped pair increments (a lower bound)"},
+                "e2e": {"value": N * N / sec, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(4 * N * (g1 - g0)),
+                        "note": "nq_matrix_tile: dense u32 counts of every tile copied to the host"},
                 "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -649,6 +676,8 @@ def run_contract(args):
     stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream shared by torch and the library
     torch.cuda.set_stream(stream)
     ctx = niqki_b200.Context(local, stream)
+    # the ranks of one box share its cores: each rank's packer gets its share
+    ctx.set_host_packing(-1, max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))))
     ix = niqki_b200.Index(S=S, K=K, W=W, H=H, min_fract=J, ctx=ctx)
     F = ix.F
     comm = Comm(ctx, rank, world, torch_bcast_bytes(dist, dev)) if world > 1 else None
@@ -845,9 +874,11 @@ def run_contract(args):
                          "hbm": {"achieved": scan_gbases, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": scan_gbases / hbm_peak if scan_gbases else None,
                                  "note": "1 B/base algorithmic: this kernel is not HBM-bound"}},
-            "roofline_query": {"kernel": "slab_resolve_kernel + query_slab_kernel", "bound": "hbm", "achieved": q_gbs, "peak": hbm_peak,
+            "roofline_query": {"kernel": "query_count_seg_kernel (CSR segment-table form: probed lists of <= 12 ids)" if G * 7.1e-4 <= 12
+                               else "slab_resolve_kernel + query_slab_kernel (granule form)", "bound": "hbm", "achieved": q_gbs, "peak": hbm_peak,
                                "unit": "GB/s", "frac": (q_gbs / hbm_peak) if q_gbs else None,
-                               "traffic": _ncu_traffic("query_slab_kernel", G, nq_total), "peak_source": peak_src,
+                               "traffic": _ncu_traffic("query_count_seg_kernel" if G * 7.1e-4 <= 12 else "query_slab_kernel", G, nq_total),
+                               "peak_source": peak_src,
                                "algorithmic_bytes": q_bytes, "gathered_postings": gathered,
                                "launches": int(q_n), "ms_per_launch": q_ms / max(q_n, 1)},
             "roofline_build": {"kernel": "cell_build_kernel", "bound": "hbm", "achieved": b_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -714,11 +714,13 @@ static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, un
     if (form == kFormStream || !a.parts) return launch_query_t<IT, kGlobal32, 512>(0, nb, a, q0, st, occ);
     return launch_query_seg_t<IT, kGlobal32, 512, 32, 96>(0, nb, a, q0, st, occ);
   }
+#ifdef NQ_TUNING  // two-queries-per-CTA CSR forms: measured within 2 % of seg8 (r01), measurement builds only
   if (form == kFormDual8 || form == kFormDual16) {
     const size_t dsmem = (size_t)ix->n * 4 + 128;  // one u32 per genome + the dummy words
     if (form == kFormDual8) return launch_query_seg_t<IT, kDual16, 256, 8, 64>(dsmem, nb, a, q0, st, occ);
     return launch_query_seg_t<IT, kDual16, 256, 16, 64>(dsmem, nb, a, q0, st, occ);
   }
+#endif
   // shards between "small" and "one CTA per SM": four 256-thread CTAs per SM while their counters + tables
   // leave >= 40 KB of L1 (n <= ~20k packed), two 512-thread CTAs while they leave >= 48 KB (n <= ~38k).  10k
   // queries vs 16k / 20k / 25k / 35k genomes: 12.9 / ~14 / 15.5 / 18.3 ms as one 1024-thread CTA per SM ->
@@ -738,13 +740,22 @@ static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, un
   const size_t occ128 = std::min<size_t>(8, (228 * 1024) / cta128);
   const bool l1_starved = 228 * 1024 - occ128 * cta128 < 24 * 1024;
   const bool nt256 = nt_env ? atoi(nt_env) == 256 : (l1_starved || a.nq_total >= (uint64_t)ix->ctx->sm_count * 36);
-#define NQ_SEG_DISPATCH(MODE)                                                                                      \
-  if (small) {                                                                                                     \
-    if (form == kFormSeg8 && nt256) return launch_query_seg_t<IT, MODE, 256, 8, 64>(smem, nb, a, q0, st, occ);     \
-    if (form == kFormSeg8) return launch_query_seg_t<IT, MODE, 128, 8, 64>(smem, nb, a, q0, st, occ);              \
+#ifdef NQ_TUNING  // seg16 / seg32 / stream at 128 threads: selectable in measurement builds only
+#define NQ_SMALL_OTHER_FORMS(MODE)                                                                                 \
     if (form == kFormSeg16) return launch_query_seg_t<IT, MODE, 128, 16, 64>(smem, nb, a, q0, st, occ);            \
     if (form == kFormSeg32) return launch_query_seg_t<IT, MODE, 128, 32, 64>(smem, nb, a, q0, st, occ);            \
-    return launch_query_t<IT, MODE, 128>(smem, nb, a, q0, st, occ);                                                \
+    if (form == kFormStream && seg_ok_) return launch_query_t<IT, MODE, 128>(smem, nb, a, q0, st, occ);
+#else
+#define NQ_SMALL_OTHER_FORMS(MODE)
+#endif
+  const bool seg_ok_ = (uint64_t)ix->p.F * ix->row_stride < (1ull << 32);
+  (void)seg_ok_;
+#define NQ_SEG_DISPATCH(MODE)                                                                                      \
+  if (small) {                                                                                                     \
+    NQ_SMALL_OTHER_FORMS(MODE)                                                                                     \
+    if (form != kFormStream && nt256) return launch_query_seg_t<IT, MODE, 256, 8, 64>(smem, nb, a, q0, st, occ);   \
+    if (form != kFormStream) return launch_query_seg_t<IT, MODE, 128, 8, 64>(smem, nb, a, q0, st, occ);            \
+    return launch_query_t<IT, MODE, 128>(smem, nb, a, q0, st, occ); /* 64-bit directory indexes */                 \
   }                                                                                                                \
   if (mid256) return launch_query_seg_t<IT, MODE, 256, 16, 64>(smem, nb, a, q0, st, occ);                          \
   if (mid512) return launch_query_seg_t<IT, MODE, 512, 16, 96>(smem, nb, a, q0, st, occ);                          \
@@ -756,6 +767,7 @@ static cudaError_t launch_query_it(const nq_index* ix, int mode, size_t smem, un
   if (mode == kPack16) { NQ_SEG_DISPATCH(kPack16) }
   NQ_SEG_DISPATCH(kSmem32)
 #undef NQ_SEG_DISPATCH
+#undef NQ_SMALL_OTHER_FORMS
 }
 // slab.cu
 bool nq_slab_layout(const nq_index* ix, int& mode, size_t& smem);

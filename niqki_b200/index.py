@@ -304,5 +304,20 @@ class Index:
         check(self.L.nq_matrix_rows(self.ix, begin, end, int(wrap16), _ptr(out)))
         return out[: end - begin, :n]
 
+    def matrix_tile(self, row_sketches, wrap16: bool = True):
+        """One tile of the genome x genome grid: counts [rows][n_shard] of the given row sketches (device
+        int32 [rows][F], from any shard) against this shard's columns (nq_matrix_tile)."""
+        rows = int(row_sketches.shape[0])
+        n = self.genome_numbers
+        out = np.zeros((max(rows, 1), max(n, 1)), np.uint32)
+        self._fence_in(row_sketches)
+        check(self.L.nq_matrix_tile(self.ix, _ptr(row_sketches), rows, int(wrap16), _ptr(out)))
+        return out[:rows, :n]
+
+    def index_sketches(self, begin: int, end: int, out):
+        """Sketches of local genomes [begin, end) rebuilt from the posting lists into ``out`` (device)."""
+        check(self.L.nq_index_sketches_device(self.ix, begin, end, _ptr(out)))
+        return out
+
     def query_matrix(self, wrap16: bool = True):
         return self.query_range(0, self.genome_numbers, wrap16)

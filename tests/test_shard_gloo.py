@@ -67,3 +67,26 @@ def test_world2_and_world3_equal_single(tmp_path, J):
         for k in ("ptr", "counts", "gids"):
             assert np.array_equal(one[k], w[k]), (world, k)
     assert one["gids"].size > 0
+
+
+def test_merge_hits_through_the_c_abi_equals_the_numpy_merge():
+    """niqki_b200.shard.merge_hits (nq_hits_from_arrays + nq_hits_merge, host code of the product library)
+    against the numpy statement of the same merge."""
+    from niqki_b200.shard import merge_hits
+
+    rng = np.random.default_rng(5)
+    nq = 23
+    parts = []
+    for s in range(4):
+        ptr, c, g = [0], [], []
+        for q in range(nq):
+            k = int(rng.integers(0, 5))
+            gs = rng.choice(np.arange(s * 500, (s + 1) * 500), size=k, replace=False)
+            cs = rng.integers(1, 7, size=k)
+            for i in np.lexsort((gs, cs))[::-1]:
+                c.append(int(cs[i])); g.append(int(gs[i]))
+            ptr.append(len(c))
+        parts.append((np.array(ptr, np.uint64), np.array(c, np.uint32), np.array(g, np.uint32)))
+    a = merge_hits(parts)
+    b = merge_hit_lists(parts, nq)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
