@@ -172,13 +172,18 @@ inline uint32_t pack_block(const uint8_t* src, uint64_t at, uint64_t nbytes, uin
   if (at + 512 <= nbytes) {
 #if defined(__x86_64__)
     if (LEVEL == 2) {
+      alignas(64) uint64_t cw[16];  // the block's 128 bytes of codes, written with streaming stores (no read-for-ownership)
       for (int k = 0; k < 8; ++k) {
-        uint64_t lo, hi, o;
-        pack64_avx512(src + at + 64 * k, lo, hi, o);
-        codes[4 * k] = (uint32_t)lo; codes[4 * k + 1] = (uint32_t)(lo >> 32);
-        codes[4 * k + 2] = (uint32_t)hi; codes[4 * k + 3] = (uint32_t)(hi >> 32);
+        uint64_t o;
+        pack64_avx512(src + at + 64 * k, cw[2 * k], cw[2 * k + 1], o);
         oth[4 * k] = (uint16_t)o; oth[4 * k + 1] = (uint16_t)(o >> 16); oth[4 * k + 2] = (uint16_t)(o >> 32); oth[4 * k + 3] = (uint16_t)(o >> 48);
         any |= (o != 0);
+      }
+      if ((reinterpret_cast<uintptr_t>(codes) & 63) == 0) {
+        _mm512_stream_si512(reinterpret_cast<__m512i*>(codes), _mm512_load_si512(cw));
+        _mm512_stream_si512(reinterpret_cast<__m512i*>(codes + 16), _mm512_load_si512(cw + 8));
+      } else {
+        memcpy(codes, cw, 128);
       }
       return any;
     }
@@ -247,10 +252,16 @@ uint64_t nq_pack_host(const char* bases, uint64_t nbytes, const uint64_t* rec_of
         }
       }
     }
+#if defined(__x86_64__)
+    _mm_sfence();  // streaming stores of this worker are visible before it reports done
+#endif
   };
   const unsigned nt = (unsigned)(tasks < threads ? (tasks ? tasks : 1) : threads);
   if (nt <= 1) work();
   else Workers::get().run(nt - 1, work);
+#if defined(__x86_64__)
+  _mm_sfence();  // (each worker's streaming stores are ordered by its own exit from run(); this covers the caller's)
+#endif
   // sparse `other` masks: the flagged blocks, in stream order
   uint64_t used = 0;
   for (uint64_t t = 0; t < tasks; ++t) {
