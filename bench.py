@@ -2,17 +2,20 @@
 """bench.py — NIQKI hot path on B200: sketch -> index -> query, whole job per step.
 
 Contract (one JSON line on rank 0):  python bench.py --gpus N --steps K --warmup W
-  N=1 workload = BASELINE.json configs[1]: 10k synthetic 5 Mbp genomes --index, then --query 1k
-  mutated copies, K=31 S=15 W=12 H=4, minjac 0.1 (the value the metric line is quoted with).
-  N>1 = the same shard per GPU (weak scaling): rank r indexes genomes [r*G,(r+1)*G), sketches its
-  slice of the queries, all ranks all-gather the query sketches over NCCL and count them against
-  their own shard; N=8 uses 12.5k genomes + 1250 queries per GPU = configs[2] exactly.
-A step = one full pass: sketch the shard's genomes, build its index, sketch + all-gather the
-queries, count/threshold them.  `value` = bases sketched by all ranks / max-over-ranks step time
-with the sequences resident in HBM; `e2e` = the same job through the host-buffer C ABI calls
-(pinned host sequences copied in, sorted hit lists copied out, every step).
---impl reference times the reference's own CPU path (oracle/_ref, else the oracle port) on a
-bounded sample with all host threads.
+  Every GPU runs BASELINE.json configs[1] at every N (weak scaling): 10k synthetic 5 Mbp genomes --index,
+  then --query 1k mutated copies, K=31 S=15 W=12 H=4, minjac 0.1.  Rank r indexes genomes [r*G,(r+1)*G)
+  (index sharded by genome id), sketches its slice of the queries, the query sketches are all-gathered
+  through the library's own exchange step (nq_allgather_sketches: NCCL behind the C ABI, u16 on the wire),
+  every shard counts all of them, the sorted per-shard hit lists go to the host and are merged on rank 0
+  (nq_hits_merge) — all inside the timed step.  `value` = bases sketched by all ranks / max-over-ranks
+  step time with the sequences resident in HBM; `e2e` = the same job through the host-buffer C ABI (pinned
+  host characters in — packed to 2 bits per base by the library on the way —, exchange, merged hits out).
+  The same line carries `query_100k`: query sketches/s of 10k queries against a 100k-genome index sharded
+  over the N GPUs (strong scaling; BASELINE's second metric), `parity_ok` (merged hit lists against a
+  brute-force count) and the rooflines.
+--workload q100k / c4 / c5: secondary lines (query-only shapes; configs[3] reads; configs[4] --matrix tiles).
+--impl reference times the reference's own CPU path (oracle/_ref, else the oracle port) on a bounded
+sample with all host threads.
 """
 import argparse
 import ctypes as C

@@ -741,3 +741,28 @@ def test_import_of_unsorted_lists(nb, ctx):
     assert np.array_equal(ptr, ohp) and np.array_equal(c, oc) and np.array_equal(gid, og)
     s2, g2 = g.export_postings()
     assert np.array_equal(s2, sizes) and np.array_equal(g2, ogids)   # lists come back gid-ascending
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_query_over_processes_equals_single_gpu(tmp_path, world):
+    """One process per GPU under torch.distributed.run: index sharded by genome id, query sketches
+    all-gathered by nq_allgather_sketches (NCCL behind the C ABI), hit lists merged by nq_hits_merge —
+    the merged (ptr, counts, gids) must equal the single-GPU answer.  Skipped with fewer GPUs."""
+    import os
+    import socket
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} CUDA devices")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = tmp_path / "result.txt"
+    cfg = dict(n=3001, S=10, nq=37, J=0.05, seed=world, out=str(out))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "_gpu_shard_worker.py"), json.dumps(cfg)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert out.read_text() == "OK"
