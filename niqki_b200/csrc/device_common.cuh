@@ -16,7 +16,7 @@ struct DevParams {
   uint32_t range;
   uint64_t kmask;     // 4^K - 1  (min %= offsetUpdatekmer, :228)
   uint32_t rc_shift;  // 2K-2     (:235)
-  uint32_t filter;    // scan kernel: read the cell before the atomicMin
+  uint32_t filter;    // scan kernel, sketch in HBM: bits 0-7 = bits per cell of the coarse shared-memory filter (0, 4, 8), bit 8 = read the cell before the atomicMin
 };
 
 // x = ((x>>32)^x) * C  — one round of the xorshift-multiply mixers (:292-293, :301-302)

@@ -69,9 +69,9 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_kernel(const uint8_t* __res
   if (SMEM)
     for (uint32_t i = threadIdx.x; i < P.F; i += NT) ssk[i] = kEmpty;
   else
-    for (uint32_t i = threadIdx.x; i < P.F * P.filter / 32; i += NT) ssk[i] = 0xFFFFFFFFu;  // filter: "anything may still win"
+    for (uint32_t i = threadIdx.x; i < P.F * (P.filter & 0xFFu) / 32; i += NT) ssk[i] = 0xFFFFFFFFu;  // filter: "anything may still win"
   __syncthreads();
-  SketchSink<SMEM> sink{SMEM ? ssk : grow, reinterpret_cast<uint8_t*>(ssk), P.filter, P.filter ? P.W - P.filter : 0u};
+  SketchSink<SMEM> sink{SMEM ? ssk : grow, reinterpret_cast<uint8_t*>(ssk), P.filter & 0xFFu, (P.filter & 0xFFu) ? P.W - (P.filter & 0xFFu) : 0u, P.filter >> 8};
 
   // this thread's run of k-mer starts [lo, hi): 16-byte aligned slices of the span
   const uint64_t base = A & ~15ull;
@@ -422,7 +422,7 @@ DevParams nq_make_dev_params(const nq_params* p) { return make_dev_params(p); }
 template <bool SMEM, int NT, bool RC_HI, bool SMALL_REM, bool DEF>
 static int launch_scan_t(nq_ctx* ctx, const DevParams& P, const uint8_t* d_bases, const uint64_t* d_offsets,
                          const Span* d_spans, uint64_t nblocks, uint32_t* d_sk) {
-  const size_t smem = SMEM ? (size_t)P.F * 4 : (size_t)P.F * P.filter / 8;  // sketch, or the coarse filter of the global form
+  const size_t smem = SMEM ? (size_t)P.F * 4 : (size_t)P.F * (P.filter & 0xFFu) / 8;  // sketch, or the coarse filter of the global form
   auto kern = sketch_scan_kernel<SMEM, NT, RC_HI, SMALL_REM, DEF>;
   NQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NqTimer timer(ctx, NQK_SCAN);
@@ -554,6 +554,9 @@ int nq_launch_sketch(nq_ctx* ctx, const nq_params* p, const char* d_bases, uint6
       if (P.W >= 8 && (size_t)P.F <= room) PG.filter = 8;
       else if (P.W >= 4 && (size_t)P.F / 2 <= room) PG.filter = 4;
     }
+    // bit 8: read the cell before the atomic — only when no coarse filter stands in front of it
+    static const char* gr = nq_tuning_env("NQ_SCAN_GREAD");  // "1" / "0": force (measurement only)
+    if (gr ? gr[0] == '1' : PG.filter == 0) PG.filter |= 0x100u;
     st = small ? launch_scan<false, 128>(ctx, PG, b, d_offsets, d_spans, nblocks, sk)
                : launch_scan<false, 1024>(ctx, PG, b, d_offsets, d_spans, nblocks, sk);
   }

@@ -27,6 +27,7 @@ struct SketchSink {
   // i.e. a more permissive filter — every value ever stored is the top bits of a submitted fingerprint.
   uint8_t* filt;
   uint32_t fbits, cshift;
+  uint32_t gread;  // global form: read the cell before the atomic (only without the coarse filter, see update())
   __device__ __forceinline__ void update(uint32_t b, uint32_t fp) const {
     // sketch[b] = min(sketch[b], fp) with empty = 0xFFFFFFFF (:350-355).
     if (SMEM) {
@@ -43,9 +44,16 @@ struct SketchSink {
         if (c > cur) return;
         if (c < cur) filt[b >> 1] = (uint8_t)((byte & ~(15u << sh)) | (c << sh));
       }
-      // global memory: a plain read filters out the k-mers that cannot lower the cell; a
-      // stale read only makes the filter conservative because cells never increase
-      if (fp < sk[b]) atomicMin(&sk[b], fp);
+      // global memory.  Without the coarse filter a plain read keeps the k-mers that cannot lower the cell
+      // away from the L2 atomic unit (a stale read only makes that conservative: cells never increase).
+      // Behind the coarse filter only ~20 % of the k-mers get here, and the read is what hurts: a dependent
+      // L2 round trip in front of every survivor, three per 16 bases and warp — so they go out as
+      // fire-and-forget RED.MIN instead.
+      if (gread) {
+        if (fp < sk[b]) atomicMin(&sk[b], fp);
+      } else {
+        atomicMin(&sk[b], fp);
+      }
     }
   }
 };

@@ -101,9 +101,9 @@ __global__ void __launch_bounds__(NT, 1) sketch_scan_packed_kernel(PackedIn in, 
   if (SMEM)
     for (uint32_t i = threadIdx.x; i < P.F; i += NT) ssk[i] = kEmpty;
   else
-    for (uint32_t i = threadIdx.x; i < P.F * P.filter / 32; i += NT) ssk[i] = 0xFFFFFFFFu;
+    for (uint32_t i = threadIdx.x; i < P.F * (P.filter & 0xFFu) / 32; i += NT) ssk[i] = 0xFFFFFFFFu;
   __syncthreads();
-  KmerEmit<SMEM, DEF, SMALL_REM> emit{{SMEM ? ssk : grow, reinterpret_cast<uint8_t*>(ssk), P.filter, P.filter ? P.W - P.filter : 0u},
+  KmerEmit<SMEM, DEF, SMALL_REM> emit{{SMEM ? ssk : grow, reinterpret_cast<uint8_t*>(ssk), P.filter & 0xFFu, (P.filter & 0xFFu) ? P.W - (P.filter & 0xFFu) : 0u, P.filter >> 8},
                                        32 - P.S, DEF ? 255u : P.mask_M, DEF ? 15u : P.maxrem, DEF ? 8u : P.M};
 
   // this thread's run of k-mer starts [lo, hi): whole 16-base words except at the ends of the span
@@ -187,7 +187,7 @@ using namespace nq;
 template <bool SMEM, int NT>
 static int launch_packed(nq_ctx* ctx, const DevParams& P, const PackedIn& in, const uint64_t* d_offsets, const Span* d_spans,
                          uint64_t nblocks, uint32_t* d_sk) {
-  const size_t smem = SMEM ? (size_t)P.F * 4 : (size_t)P.F * P.filter / 8;
+  const size_t smem = SMEM ? (size_t)P.F * 4 : (size_t)P.F * (P.filter & 0xFFu) / 8;
   const bool def = P.K == 31 && P.M == 8 && P.mask_M == 255 && P.maxrem == 15, small_rem = P.maxrem <= 32;
   NqTimer timer(ctx, NQK_SCAN);
 #define NQ_LAUNCH(DEFV, SR)                                                                              \
@@ -261,6 +261,7 @@ int nq_launch_sketch_packed(nq_ctx* ctx, const nq_params* p, const uint32_t* d_c
       if (P.W >= 8 && (size_t)P.F <= room) P.filter = 8;
       else if (P.W >= 4 && (size_t)P.F / 2 <= room) P.filter = 4;
     }
+    if (P.filter == 0) P.filter |= 0x100u;  // no coarse filter: read the cell before the atomic (sketch_common.cuh)
     st = small ? launch_packed<false, 128>(ctx, P, in, nullptr, d_spans, spans.size(), sk)
                : launch_packed<false, 1024>(ctx, P, in, nullptr, d_spans, spans.size(), sk);
   }
