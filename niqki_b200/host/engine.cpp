@@ -378,8 +378,6 @@ void Engine::build_index() {
     std::vector<uint32_t> sizes, gids;
     export_all(sizes, gids);
     // the new sketches, in gid order, on the host
-    std::vector<std::pair<uint32_t, const Segment*>> order;
-    std::vector<int> owner;
     struct Seg { uint32_t gid0, count; int dev; uint64_t row; };
     std::vector<Seg> segs;
     for (int t = 0; t < n; ++t)
