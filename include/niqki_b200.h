@@ -218,7 +218,8 @@ int nq_comm_destroy(nq_comm* c);
 int nq_comm_info(const nq_comm* c, int* rank, int* nranks, int* nccl_version);
 int nq_shard_range(uint64_t n, int nranks, int rank, uint64_t* begin, uint64_t* end);
 /* every rank contributes n_local sketches int32[n_local][F] (device); all receive
- * int32[nranks*n_local][F] in rank order */
+ * int32[nranks*n_local][F] in rank order.  n_local must be the same on every rank (a rank with
+ * fewer queries pads its block with rows of -1, which probe nothing) */
 int nq_allgather_sketches(nq_comm* c, const nq_params* p, const int32_t* d_local, uint64_t n_local, int32_t* d_all);
 int nq_bcast_sketches(nq_comm* c, const nq_params* p, int32_t* d_sketches, uint64_t n, int root);
 /* per-shard results of the same query batch -> one result, each query sorted (count, gid) descending */
