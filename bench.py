@@ -42,7 +42,7 @@ METRIC = "Gbases/s sketched (configs[1] per GPU: index 10k x 5 Mbp genomes + que
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genomes", type=int, default=0, help="genomes per GPU (default: 10000 = configs[1], at every N)")
